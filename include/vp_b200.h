@@ -1,0 +1,116 @@
+/* vp_b200 — C ABI of the B200-native denoising hot path of VideoPainter (CogVideoX-5B-I2V backbone + context-encoder
+ * branch).  This header is the drop-in boundary: every entry point replaces one piece of the reference's eager-PyTorch
+ * path and is what a binding from the reference's Python (ctypes / torch custom-op) calls.  INTEGRATION.md shows the
+ * reference-side stubs.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless stated otherwise; bf16 tensors are passed as `const void*`
+ *   - `stream` is a cudaStream_t (the caller's current stream); nothing here allocates, synchronises or blocks the host
+ *   - return value: 0 = ok, <0 = error (VP_ERR_*); vp_last_error() gives the text, vp_last_cuda_error() the cudaError_t
+ *   - there is no CPU path and no alternate backend: unsupported shapes are errors
+ *
+ * Reference files (relative to /root/reference/diffusers/src/diffusers/models):
+ *   T3D = transformers/cogvideox_transformer_3d.py   BR = branch_cogvideox.py   AP = attention_processor.py
+ *   NRM = normalization.py   EMB = embeddings.py   ATT = attention.py   ACT = activations.py
+ */
+#ifndef VP_B200_H
+#define VP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VP_OK 0
+#define VP_ERR_BAD_SHAPE (-1)
+#define VP_ERR_BAD_ALIGN (-2)
+#define VP_ERR_UNSUPPORTED (-3)
+#define VP_ERR_CUDA (-4)
+#define VP_ERR_DRIVER (-5)
+
+int vp_version(void);
+const char* vp_last_error(void);       /* host string, valid until the next failing call on this thread */
+int vp_last_cuda_error(void);
+
+/* Timesteps / get_timestep_embedding (EMB:27-78, 777-793): out[b] = [cos(t w) | sin(t w)] (flip) in fp32.
+ * Exactly one of t_i64 / t_f32 is non-null. */
+int vp_time_sinusoid(const int64_t* t_i64, const float* t_f32, float* out, int batch, int dim, int flip_sin_to_cos,
+                     float freq_shift, void* stream);
+
+/* out[b, n] = sum_k act(in[b, k]) W[n, k] + bias[n]; act = SiLU when act_silu != 0.  fp32 activations, bf16 weights.
+ * Replaces TimestepEmbedding.linear_1/linear_2 (EMB:762-774), CogVideoXLayerNormZero.linear(silu(temb)) (NRM:376) and
+ * AdaLayerNorm.linear(silu(temb)) (NRM:73).  batch <= 8. */
+int vp_gemv(const float* in, const void* weight, const void* bias, float* out, int batch, int n, int k, int act_silu,
+            void* stream);
+
+/* CogVideoXLayerNormZero modulation (NRM:377-378) over the joint (text | video) sequence:
+ *   y[b, s] = LN(x[b, s]; gamma, beta, eps) * (1 + mod[b, scale_off(s)]) + mod[b, shift_off(s)]
+ * where the text expert offsets are used for s < text_len.  x rows are read at (b * x_batch_rows + x_row_offset + s);
+ * y is compact [batch * rows_per_batch, dim].  mod may be null (plain affine LayerNorm). */
+int vp_ln_modulate(const void* x, long long x_batch_rows, int x_row_offset, void* y, int batch, int rows_per_batch, int dim,
+                   const void* gamma, const void* beta, float eps, const float* mod, long long mod_batch_stride,
+                   int shift_video_off, int scale_video_off, int shift_text_off, int scale_text_off, int text_len,
+                   void* stream);
+
+/* Final head normalisation (T3D:613-624): y = LN(LN(x; g1, b1); g2, b2) * (1 + mod[b, scale_off]) + mod[b, shift_off]
+ * (norm_final, then AdaLayerNorm with chunk order shift, scale: NRM:78). */
+int vp_ln_final(const void* x, long long x_batch_rows, int x_row_offset, void* y, int batch, int rows_per_batch, int dim,
+                const void* gamma1, const void* beta1, const void* gamma2, const void* beta2, float eps, const float* mod,
+                long long mod_batch_stride, int shift_off, int scale_off, void* stream);
+
+/* tcgen05 GEMMs  C[M, N] = A[M, K] W[N, K]^T  (nn.Linear layout), bf16 in, fp32 accumulate, fused epilogues.
+ * Logical row m maps to batch b = m / rows_per_batch and token s = m % rows_per_batch; the output row is
+ * (b * out_batch_rows + out_row_offset + s) and rows with s + out_row_offset < 0 are dropped.  N % 64 == 0, K % 8 == 0. */
+
+/* out = (A W^T + bias) * alpha            — text_proj (EMB:408), proj_out (T3D:624), branch_blocks (BR:416-421) */
+int vp_gemm_bias(const void* a, long long lda, const void* w, long long ldw, const void* bias, void* out, int ldo, int m,
+                 int n, int k, int rows_per_batch, long long out_batch_rows, int out_row_offset, float alpha, void* stream);
+
+/* out = gelu_tanh(A W^T + bias)            — FeedForward.net[0] (ATT:1200, ACT:83) */
+int vp_gemm_gelu(const void* a, long long lda, const void* w, long long ldw, const void* bias, void* out, int ldo, int m,
+                 int n, int k, void* stream);
+
+/* out = res + gate[b, expert(s)] * (A W^T + bias) [+ inject[b, s - text_len] where inject_mask == 0]
+ * — attention out-proj + gated residual (AP:2202, T3D:169-170), FFN-2 + gated residual + branch injection
+ * (ATT:1201, T3D:181-182, 596-609), and patch-embed conv + positional table (EMB:410-451; gate = null).
+ * gate is fp32: gate[b * gate_batch_stride + (s < text_len ? gate_text_off : gate_video_off) + n]. */
+int vp_gemm_gate_residual(const void* a, long long lda, const void* w, long long ldw, const void* bias, void* out, int ldo,
+                          int m, int n, int k, int rows_per_batch, long long out_batch_rows, int out_row_offset,
+                          const void* res, int ldr, long long res_batch_rows, int res_row_offset, const float* gate,
+                          long long gate_batch_stride, int gate_video_off, int gate_text_off, int text_len,
+                          const void* inject, long long inject_batch_stride, int ldi, const uint8_t* inject_mask,
+                          int video_len, void* stream);
+
+/* Fused to_q/to_k/to_v + QK LayerNorm(64) + 3D RoPE (AP:2132-2154), written head-major [B, H, S, 64].
+ * w is [Wq; Wk; Wv] (qkv_first = 0) or [Wk; Wv] (qkv_first = 1, previous-window keys AP:2157-2172, 2247-2252).
+ * row_scale[m] (nullable) multiplies the projection before the norm (prev_resample_mask * prev_clip_weight).
+ * k2_out/v2_out (nullable) receive the masked copy of the ID-resample processor: K2 = RoPE(norm_k(k * mask2)),
+ * V2 = v * mask2 (AP:2255-2281). rope tables are fp32 [video_len, 64] (nullable). */
+int vp_gemm_qkv(const void* a, long long lda, const void* w, long long ldw, const void* bias, int m, int k, int batch_rows,
+                int heads, int qkv_first, void* q_out, void* k_out, void* v_out, void* k2_out, void* v2_out,
+                const uint8_t* mask2, const float* row_scale, const void* norm_q_w, const void* norm_q_b,
+                const void* norm_k_w, const void* norm_k_b, float qk_eps, const float* rope_cos, const float* rope_sin,
+                int text_len, void* stream);
+
+/* softmax(Q K^T * scale) V over one or two K/V segments, d_head = 64, non-causal, unmasked (AP:2192-2197, 2285-2290).
+ * q [B, H, seq_q, 64], k0/v0/k1/v1 [B, H, kv_len, 64]; out [B, seq_q, ldo] with head h at columns [64h, 64h + 64).
+ * out = (accumulate ? out : 0) + out_scale * attention   (previous-window blend, AP:2176-2189). */
+int vp_attention(const void* q, const void* k0, const void* v0, int kv_len0, const void* k1, const void* v1, int kv_len1,
+                 void* out, int ldo, int batch, int heads, int seq_q, float softmax_scale, float out_scale, int accumulate,
+                 void* stream);
+
+/* CogVideoXPatchEmbed.proj input gather (EMB:404-414): A[(b f y x), c*4 + dy*2 + dx] from [BF, C0(+C1), H, W];
+ * the two sources are concatenated along channels (BR:359); columns >= 4 (C0 + C1) are zero. */
+int vp_patchify(const void* src0, int c0, const void* src1, int c1, int bf, int h, int w, void* out, int kpad, void* stream);
+
+/* masks -> (avg_pool2d(mask, 2) > 0) per patch (EMB:417-426); mask is bf16 [BF, 1, H, W], out uint8 [BF * H/2 * W/2] */
+int vp_mask_pool(const void* mask, int bf, int h, int w, uint8_t* out, void* stream);
+
+/* unpatchify (T3D:630-632): proj [(b f y x), C*4] -> out [BF, C, H, W] */
+int vp_unpatchify(const void* proj, int bf, int c, int h, int w, void* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VP_B200_H */

@@ -1,0 +1,23 @@
+// Parameter block shared by attention.cu (kernel) and capi.cu (C ABI).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vp {
+
+struct AttnParams {
+  int batch, heads;
+  int seq_q;                 // query rows per (batch, head)
+  int kv_len0, kv_len1;      // keys in segment 0 / segment 1 (0 = absent)
+  float scale_log2;          // softmax scale * log2(e)
+  __nv_bfloat16* out;        // [batch, seq_q, ldo]; head h occupies columns [h*64, h*64+64)
+  int ldo;
+  float out_scale;           // out = (accumulate ? out : 0) + out_scale * softmax(QKᵀ)V   (prev-window blend AP:2176-2189)
+  int accumulate;
+};
+
+int launch_attention(const void* q, const void* k0, const void* v0, const void* k1, const void* v1, const AttnParams& p,
+                     cudaStream_t st);
+
+}  // namespace vp

@@ -1,0 +1,362 @@
+// HBM-bound token-wise kernels of the denoising step: expert adaLN-zero modulation (NRM:373-379), the small
+// conditioning GEMVs (timestep MLP EMB:762-774, adaLN tables NRM:376, norm_out NRM:73), patch gathering for the
+// 2x2/stride-2 patch-embed convolution (EMB:408-414), mask pooling (EMB:417-426), the final double LayerNorm
+// (T3D:613-624) and unpatchify (T3D:630-632).
+#include "elementwise.cuh"
+#include "host_util.cuh"
+
+namespace vp {
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+  f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 u;
+  u.x = pack_bf16(f[0], f[1]); u.y = pack_bf16(f[2], f[3]);
+  u.z = pack_bf16(f[4], f[5]); u.w = pack_bf16(f[6], f[7]);
+  return u;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// LayerNorm + expert modulation.  One warp per token row; the row lives in registers (CH chunks of 8 bf16 per lane),
+// statistics in fp32 (two-pass on registers), 16-byte loads and stores, text/video expert selected per row.
+//   y = LN(x; gamma, beta, eps) * (1 + scale[b, e]) + shift[b, e]        e = text if s < text_len else video
+// ------------------------------------------------------------------------------------------------------------------
+template <int CH>
+__global__ void __launch_bounds__(256) ln_modulate_kernel(const LnModParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + warp;
+  if (row >= p.rows) return;
+  const int b = (int)(row / p.rows_per_batch);
+  const int s = (int)(row - (long long)b * p.rows_per_batch);
+  const __nv_bfloat16* x = p.x + ((long long)b * p.x_batch_rows + p.x_row_offset + s) * p.D;
+  __nv_bfloat16* y = p.y + row * p.D;
+  const int nchunk = p.D >> 3;   // 8-element chunks in the row
+
+  float v[CH][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    const int c = lane + i * 32;
+    if (c < nchunk) {
+      unpack8(ldg_nc_v4(x + c * 8), v[i]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sum += v[i][e];
+    }
+  }
+  const float mean = warp_sum(sum) / (float)p.D;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    const int c = lane + i * 32;
+    if (c < nchunk) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float d = v[i][e] - mean;
+        sq += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / (float)p.D + p.eps);
+
+  const bool text = s < p.text_len;
+  const float* shift = p.mod ? p.mod + (long long)b * p.mod_batch_stride + (text ? p.shift_text_off : p.shift_video_off) : nullptr;
+  const float* scale = p.mod ? p.mod + (long long)b * p.mod_batch_stride + (text ? p.scale_text_off : p.scale_video_off) : nullptr;
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    const int c = lane + i * 32;
+    if (c < nchunk) {
+      float g[8], be[8], o[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(p.gamma) + c), g);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(p.beta) + c), be);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = (v[i][e] - mean) * rstd * g[e] + be[e];
+      if (shift) {
+        const float4 s0 = __ldg(reinterpret_cast<const float4*>(shift + c * 8));
+        const float4 s1 = __ldg(reinterpret_cast<const float4*>(shift + c * 8) + 1);
+        const float4 c0 = __ldg(reinterpret_cast<const float4*>(scale + c * 8));
+        const float4 c1 = __ldg(reinterpret_cast<const float4*>(scale + c * 8) + 1);
+        o[0] = o[0] * (1.f + c0.x) + s0.x; o[1] = o[1] * (1.f + c0.y) + s0.y;
+        o[2] = o[2] * (1.f + c0.z) + s0.z; o[3] = o[3] * (1.f + c0.w) + s0.w;
+        o[4] = o[4] * (1.f + c1.x) + s1.x; o[5] = o[5] * (1.f + c1.y) + s1.y;
+        o[6] = o[6] * (1.f + c1.z) + s1.z; o[7] = o[7] * (1.f + c1.w) + s1.w;
+      }
+      *reinterpret_cast<uint4*>(y + c * 8) = pack8(o);
+    }
+  }
+}
+
+// Final head normalisation: y = LN2(LN1(x)) * (1 + scale[b]) + shift[b] on the video rows only (T3D:613-624).
+template <int CH>
+__global__ void __launch_bounds__(256) ln_double_kernel(const LnModParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + warp;
+  if (row >= p.rows) return;
+  const int b = (int)(row / p.rows_per_batch);
+  const int s = (int)(row - (long long)b * p.rows_per_batch);
+  const __nv_bfloat16* x = p.x + ((long long)b * p.x_batch_rows + p.x_row_offset + s) * p.D;
+  __nv_bfloat16* y = p.y + row * p.D;
+  const int nchunk = p.D >> 3;
+  const float invD = 1.0f / (float)p.D;
+
+  float v[CH][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    const int c = lane + i * 32;
+    if (c < nchunk) {
+      unpack8(ldg_nc_v4(x + c * 8), v[i]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sum += v[i][e];
+    }
+  }
+  float mean = warp_sum(sum) * invD;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    const int c = lane + i * 32;
+    if (c < nchunk) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { const float d = v[i][e] - mean; sq += d * d; }
+    }
+  }
+  float rstd = rsqrtf(warp_sum(sq) * invD + p.eps);
+  sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    const int c = lane + i * 32;
+    if (c < nchunk) {
+      float g[8], be[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(p.gamma) + c), g);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(p.beta) + c), be);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { v[i][e] = (v[i][e] - mean) * rstd * g[e] + be[e]; sum += v[i][e]; }
+    }
+  }
+  mean = warp_sum(sum) * invD;
+  sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    const int c = lane + i * 32;
+    if (c < nchunk) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { const float d = v[i][e] - mean; sq += d * d; }
+    }
+  }
+  rstd = rsqrtf(warp_sum(sq) * invD + p.eps);
+  const float* shift = p.mod + (long long)b * p.mod_batch_stride + p.shift_video_off;
+  const float* scale = p.mod + (long long)b * p.mod_batch_stride + p.scale_video_off;
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    const int c = lane + i * 32;
+    if (c < nchunk) {
+      float g[8], be[8], o[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(p.gamma2) + c), g);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(p.beta2) + c), be);
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        o[e] = ((v[i][e] - mean) * rstd * g[e] + be[e]) * (1.f + __ldg(scale + c * 8 + e)) + __ldg(shift + c * 8 + e);
+      *reinterpret_cast<uint4*>(y + c * 8) = pack8(o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// out[b, n] = sum_k act(in[b, k]) * W[n, k] + bias[n]   (fp32 in/out, bf16 weights), one warp per output column.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int GEMV_MAX_B = 8;
+__global__ void __launch_bounds__(256) gemv_kernel(const float* __restrict__ in, const __nv_bfloat16* __restrict__ W,
+                                                   const __nv_bfloat16* __restrict__ bias, float* __restrict__ out, int B,
+                                                   int N, int K, int act_silu) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * 8 + warp;
+  if (n >= N) return;
+  float acc[GEMV_MAX_B];
+#pragma unroll
+  for (int b = 0; b < GEMV_MAX_B; ++b) acc[b] = 0.f;
+  const __nv_bfloat16* w = W + (long long)n * K;
+  for (int k0 = lane * 8; k0 < K; k0 += 256) {
+    float wf[8];
+    unpack8(ldg_nc_v4(w + k0), wf);
+#pragma unroll
+    for (int b = 0; b < GEMV_MAX_B; ++b) {
+      if (b < B) {
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(in + (long long)b * K + k0));
+        const float4 a1 = __ldg(reinterpret_cast<const float4*>(in + (long long)b * K + k0) + 1);
+        float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float xv = act_silu ? silu(a[e]) : a[e];
+          acc[b] = fmaf(xv, wf[e], acc[b]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < GEMV_MAX_B; ++b) {
+    if (b < B) {
+      const float r = warp_sum(acc[b]);
+      if (lane == 0) out[(long long)b * N + n] = r + (bias ? __bfloat162float(bias[n]) : 0.f);
+    }
+  }
+}
+
+// sinusoidal timestep features, EMB:56-73 with flip_sin_to_cos: out[b] = [cos(t w_i) | sin(t w_i)]
+__global__ void timestep_sinusoid_kernel(const long long* __restrict__ t_i64, const float* __restrict__ t_f32,
+                                         float* __restrict__ out, int B, int dim, int flip_sin_to_cos, float freq_shift) {
+  const int half = dim / 2;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * half) return;
+  const int b = idx / half, i = idx - b * half;
+  const float t = t_i64 ? (float)t_i64[b] : t_f32[b];
+  const float w = expf(-9.210340371976184f * (float)i / ((float)half - freq_shift));   // ln(10000)
+  const float a = t * w;
+  const float sv = sinf(a), cv = cosf(a);
+  float* o = out + (long long)b * dim;
+  if (flip_sin_to_cos) { o[i] = cv; o[half + i] = sv; }
+  else { o[i] = sv; o[half + i] = cv; }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// patch gather for Conv2d(C -> D, k=2, s=2): A[(b, f, py, px), c*4 + dy*2 + dx] = src[b, f, c, 2py+dy, 2px+dx]
+// (channels may come from two tensors concatenated along C: BR:359).  Columns >= 4C are zero padding.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) patchify_kernel(const __nv_bfloat16* __restrict__ src0, int C0,
+                                                       const __nv_bfloat16* __restrict__ src1, int C1, int BF, int H, int W,
+                                                       __nv_bfloat16* __restrict__ out, int Kpad) {
+  const int ph = H / 2, pw = W / 2;
+  const long long total = (long long)BF * ph * pw * (Kpad / 2);
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int kp = (int)(idx % (Kpad / 2));            // pair index: (c, dy) with dx = 0, 1
+    long long r = idx / (Kpad / 2);
+    const int px = (int)(r % pw); r /= pw;
+    const int py = (int)(r % ph);
+    const long long bf = r / ph;
+    const int c = kp >> 1, dy = kp & 1;
+    __nv_bfloat162 v = __floats2bfloat162_rn(0.f, 0.f);
+    if (c < C0 + C1) {
+      const __nv_bfloat16* s = c < C0 ? src0 + ((bf * C0 + c) * H + (2 * py + dy)) * (long long)W + 2 * px
+                                      : src1 + ((bf * C1 + (c - C0)) * H + (2 * py + dy)) * (long long)W + 2 * px;
+      v = *reinterpret_cast<const __nv_bfloat162*>(s);
+    }
+    *reinterpret_cast<__nv_bfloat162*>(out + ((bf * ph + py) * pw + px) * (long long)Kpad + kp * 2) = v;
+  }
+}
+
+// mask [B*F, 1, H, W] (any float dtype given as bf16) -> uint8 [B*F*ph*pw] = (avg_pool2d(mask, 2) > 0)   EMB:417-426
+__global__ void mask_pool_kernel(const __nv_bfloat16* __restrict__ mask, int BF, int H, int W, uint8_t* __restrict__ out) {
+  const int ph = H / 2, pw = W / 2;
+  const long long total = (long long)BF * ph * pw;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int px = (int)(idx % pw);
+  const int py = (int)((idx / pw) % ph);
+  const long long bf = idx / ((long long)pw * ph);
+  const __nv_bfloat16* m = mask + (bf * H + 2 * py) * (long long)W + 2 * px;
+  const float s = __bfloat162float(m[0]) + __bfloat162float(m[1]) + __bfloat162float(m[W]) + __bfloat162float(m[W + 1]);
+  out[idx] = (s * 0.25f) > 0.0f ? 1 : 0;
+}
+
+// unpatchify T3D:630-632: proj[(b, f, py, px), c*4 + dy*2 + dx] -> out[b, f, c, 2py+dy, 2px+dx]
+__global__ void unpatchify_kernel(const __nv_bfloat16* __restrict__ proj, int BF, int C, int H, int W,
+                                  __nv_bfloat16* __restrict__ out) {
+  const int ph = H / 2, pw = W / 2;
+  const long long total = (long long)BF * C * H * pw;       // one thread per horizontal pixel pair
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int px = (int)(idx % pw);
+  long long r = idx / pw;
+  const int y = (int)(r % H); r /= H;
+  const int c = (int)(r % C);
+  const long long bf = r / C;
+  const int py = y >> 1, dy = y & 1;
+  const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(proj + ((bf * ph + py) * pw + px) * (long long)(C * 4) + c * 4 + dy * 2);
+  *reinterpret_cast<__nv_bfloat162*>(out + ((bf * C + c) * H + y) * (long long)W + 2 * px) = v;
+}
+
+}  // namespace
+
+int launch_ln_modulate(const LnModParams& p, cudaStream_t st) {
+  VP_REQUIRE(p.rows > 0 && p.D > 0 && p.D % 8 == 0, VP_ERR_BAD_SHAPE, "ln_modulate: D must be a positive multiple of 8");
+  VP_REQUIRE(p.D <= 4096, VP_ERR_UNSUPPORTED, "ln_modulate: D > 4096 not supported");
+  const int nchunk = p.D / 8;
+  const int ch = (nchunk + 31) / 32;
+  const unsigned grid = (unsigned)((p.rows + 7) / 8);
+  const bool dbl = p.gamma2 != nullptr;
+  if (dbl) VP_REQUIRE(p.mod != nullptr, VP_ERR_BAD_SHAPE, "ln_double: modulation table required");
+#define VP_LN_CASE(N)                                                   \
+  if (ch <= N) {                                                        \
+    if (dbl) ln_double_kernel<N><<<grid, 256, 0, st>>>(p);              \
+    else ln_modulate_kernel<N><<<grid, 256, 0, st>>>(p);                \
+    VP_CHECK_CUDA(cudaGetLastError());                                  \
+    return VP_OK;                                                       \
+  }
+  VP_LN_CASE(1)
+  VP_LN_CASE(2)
+  VP_LN_CASE(4)
+  VP_LN_CASE(8)
+  VP_LN_CASE(12)
+  VP_LN_CASE(16)
+#undef VP_LN_CASE
+  return fail(VP_ERR_UNSUPPORTED, "ln_modulate: unsupported width");
+}
+
+int launch_gemv(const float* in, const void* W, const void* bias, float* out, int B, int N, int K, int act_silu,
+                cudaStream_t st) {
+  VP_REQUIRE(B > 0 && B <= GEMV_MAX_B, VP_ERR_UNSUPPORTED, "gemv: batch must be in [1, 8]");
+  VP_REQUIRE(N > 0 && K > 0 && K % 8 == 0, VP_ERR_BAD_SHAPE, "gemv: K must be a multiple of 8");
+  gemv_kernel<<<(N + 7) / 8, 256, 0, st>>>(in, (const __nv_bfloat16*)W, (const __nv_bfloat16*)bias, out, B, N, K, act_silu);
+  VP_CHECK_CUDA(cudaGetLastError());
+  return VP_OK;
+}
+
+int launch_timestep_sinusoid(const long long* t_i64, const float* t_f32, float* out, int B, int dim, int flip, float shift,
+                             cudaStream_t st) {
+  VP_REQUIRE(B > 0 && dim > 0 && dim % 2 == 0, VP_ERR_BAD_SHAPE, "timestep: dim must be even");
+  VP_REQUIRE((t_i64 != nullptr) != (t_f32 != nullptr), VP_ERR_BAD_SHAPE, "timestep: exactly one timestep pointer");
+  const int total = B * dim / 2;
+  timestep_sinusoid_kernel<<<(total + 255) / 256, 256, 0, st>>>(t_i64, t_f32, out, B, dim, flip, shift);
+  VP_CHECK_CUDA(cudaGetLastError());
+  return VP_OK;
+}
+
+int launch_patchify(const void* src0, int C0, const void* src1, int C1, int BF, int H, int W, void* out, int Kpad,
+                    cudaStream_t st) {
+  VP_REQUIRE(BF > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, VP_ERR_BAD_SHAPE, "patchify: H and W must be even");
+  VP_REQUIRE(Kpad % 8 == 0 && Kpad >= 4 * (C0 + C1), VP_ERR_BAD_SHAPE, "patchify: Kpad too small or not a multiple of 8");
+  const long long total = (long long)BF * (H / 2) * (W / 2) * (Kpad / 2);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  patchify_kernel<<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)src0, C0, (const __nv_bfloat16*)src1, C1, BF, H, W,
+                                                   (__nv_bfloat16*)out, Kpad);
+  VP_CHECK_CUDA(cudaGetLastError());
+  return VP_OK;
+}
+
+int launch_mask_pool(const void* mask, int BF, int H, int W, uint8_t* out, cudaStream_t st) {
+  VP_REQUIRE(BF > 0 && H % 2 == 0 && W % 2 == 0, VP_ERR_BAD_SHAPE, "mask_pool: H and W must be even");
+  const long long total = (long long)BF * (H / 2) * (W / 2);
+  mask_pool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)mask, BF, H, W, out);
+  VP_CHECK_CUDA(cudaGetLastError());
+  return VP_OK;
+}
+
+int launch_unpatchify(const void* proj, int BF, int C, int H, int W, void* out, cudaStream_t st) {
+  VP_REQUIRE(BF > 0 && C > 0 && H % 2 == 0 && W % 2 == 0, VP_ERR_BAD_SHAPE, "unpatchify: H and W must be even");
+  const long long total = (long long)BF * C * H * (W / 2);
+  unpatchify_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)proj, BF, C, H, W,
+                                                                     (__nv_bfloat16*)out);
+  VP_CHECK_CUDA(cudaGetLastError());
+  return VP_OK;
+}
+
+}  // namespace vp

@@ -1,0 +1,375 @@
+// tcgen05 GEMM for the token-wise linears of CogVideoXBlock:  C[M,N] = A[M,K] · W[N,K]ᵀ  (bf16 in, fp32 accumulate)
+// with the follow-up elementwise work fused into the epilogue (see GemmEpilogue in gemm.cuh).
+//
+// Structure (one persistent CTA per SM, 256 threads):
+//   warp 0   TMA producer   : A tile 128x64 and W tile 256x64 per stage, 4-stage mbarrier ring
+//   warp 1   MMA issuer     : one thread issues tcgen05.mma 128x256x16, fp32 accumulators in TMEM
+//   warp 2   TMEM allocator : 512 columns = two 128x256 accumulator stages
+//   warp 4-7 epilogue       : tcgen05.ld (thread == row), fused epilogue, 16-byte global stores;
+//                             overlaps with the MMAs of the next tile through the second TMEM stage
+#include "gemm.cuh"
+#include "host_util.cuh"
+
+namespace vp {
+
+namespace {
+
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2;
+constexpr int B_BYTES = BN * BK * 2;
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int BAR_BYTES = 256;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;   // +1024: manual alignment slack
+constexpr int NUM_THREADS = 256;
+constexpr uint32_t TMEM_COLS = 512;
+
+__device__ __forceinline__ void tile_coords(int tile, int m_tiles, int n_tiles, int group_m, int& m_blk, int& n_blk) {
+  const int per_group = group_m * n_tiles;
+  const int g = tile / per_group;
+  const int first_m = g * group_m;
+  const int gsz = min(group_m, m_tiles - first_m);
+  const int r = tile - g * per_group;
+  m_blk = first_m + r % gsz;
+  n_blk = r / gsz;
+}
+
+__device__ __forceinline__ void load_bf16x32(const __nv_bfloat16* p, float* f) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 u = __ldg(reinterpret_cast<const uint4*>(p) + i);
+    f[i * 8 + 0] = bf16_lo(u.x); f[i * 8 + 1] = bf16_hi(u.x);
+    f[i * 8 + 2] = bf16_lo(u.y); f[i * 8 + 3] = bf16_hi(u.y);
+    f[i * 8 + 4] = bf16_lo(u.z); f[i * 8 + 5] = bf16_hi(u.z);
+    f[i * 8 + 6] = bf16_lo(u.w); f[i * 8 + 7] = bf16_hi(u.w);
+  }
+}
+__device__ __forceinline__ void store_bf16x32(__nv_bfloat16* p, const float* f) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 u;
+    u.x = pack_bf16(f[i * 8 + 0], f[i * 8 + 1]);
+    u.y = pack_bf16(f[i * 8 + 2], f[i * 8 + 3]);
+    u.z = pack_bf16(f[i * 8 + 4], f[i * 8 + 5]);
+    u.w = pack_bf16(f[i * 8 + 6], f[i * 8 + 7]);
+    reinterpret_cast<uint4*>(p)[i] = u;
+  }
+}
+
+// ---- plain / gelu / residual epilogue on 32 accumulator columns of one row -------------------------------------
+template <int EPI>
+__device__ __forceinline__ void epilogue_cols32(const GemmParams& p, const uint32_t* acc, int b, int s, int n0) {
+  float v[32];
+  if (p.bias) {
+    load_bf16x32(p.bias + n0, v);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(acc[j]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+  }
+  if (EPI == EPI_BIAS) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+  } else if (EPI == EPI_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
+  } else if (EPI == EPI_RESID) {
+    if (p.gate) {
+      const float* g = p.gate + (long long)b * p.gate_batch_stride + (s < p.text_len ? p.gate_text_off : p.gate_video_off) + n0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 gv = __ldg(reinterpret_cast<const float4*>(g) + j);
+        v[j * 4 + 0] *= gv.x; v[j * 4 + 1] *= gv.y; v[j * 4 + 2] *= gv.z; v[j * 4 + 3] *= gv.w;
+      }
+    }
+    float r[32];
+    load_bf16x32(p.res + ((long long)b * p.res_batch_rows + p.res_row_offset + s) * p.ldr + n0, r);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] += r[j];
+    if (p.inject && s >= p.text_len) {
+      const int sv = s - p.text_len;
+      if (!p.inject_mask || p.inject_mask[(long long)b * p.video_len + sv] == 0) {
+        load_bf16x32(p.inject + (long long)b * p.inject_batch_stride + (long long)sv * p.ldi + n0, r);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += r[j];
+      }
+    }
+  }
+  store_bf16x32(p.out + ((long long)b * p.out_batch_rows + p.out_row_offset + s) * p.ldo + n0, v);
+}
+
+// ---- QKV epilogue on one head (64 accumulator columns) of one row ----------------------------------------------
+__device__ __forceinline__ void ln64_rope_store(const float* x, float pre, const __nv_bfloat16* w, const __nv_bfloat16* bia,
+                                                float eps, const float* cosr, const float* sinr, __nv_bfloat16* dst) {
+  float mean = 0.f;
+#pragma unroll
+  for (int j = 0; j < 64; ++j) mean += x[j];
+  mean *= pre * (1.0f / 64.0f);
+  float var = 0.f;
+#pragma unroll
+  for (int j = 0; j < 64; ++j) {
+    float d = x[j] * pre - mean;
+    var += d * d;
+  }
+  const float rstd = rsqrtf(var * (1.0f / 64.0f) + eps);
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {   // 32 columns at a time keeps the live set small
+    float g[32], be[32], y[32];
+    load_bf16x32(w + c * 32, g);
+    load_bf16x32(bia + c * 32, be);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) y[j] = (x[c * 32 + j] * pre - mean) * rstd * g[j] + be[j];
+    if (cosr) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 cv = __ldg(reinterpret_cast<const float4*>(cosr + c * 32) + j);
+        float4 sv = __ldg(reinterpret_cast<const float4*>(sinr + c * 32) + j);
+        const float a0 = y[j * 4 + 0], a1 = y[j * 4 + 1], a2 = y[j * 4 + 2], a3 = y[j * 4 + 3];
+        // EMB:683-692: out = x*cos + rot(x)*sin, rot(x)[2i] = -x[2i+1], rot(x)[2i+1] = x[2i]
+        y[j * 4 + 0] = a0 * cv.x - a1 * sv.x;
+        y[j * 4 + 1] = a1 * cv.y + a0 * sv.y;
+        y[j * 4 + 2] = a2 * cv.z - a3 * sv.z;
+        y[j * 4 + 3] = a3 * cv.w + a2 * sv.w;
+      }
+    }
+    store_bf16x32(dst + c * 32, y);
+  }
+}
+
+__device__ __forceinline__ void epilogue_qkv_head(const GemmParams& p, const uint32_t* acc, int m, int b, int s, int n0) {
+  float x[64];
+  load_bf16x32(p.bias + n0, x);
+  load_bf16x32(p.bias + n0 + 32, x + 32);
+#pragma unroll
+  for (int j = 0; j < 64; ++j) x[j] += __uint_as_float(acc[j]);
+  const int which = n0 / p.d_model + p.qkv_first;      // 0 = Q, 1 = K, 2 = V
+  const int head = (n0 % p.d_model) >> 6;
+  const float rs = p.row_scale ? p.row_scale[m] : 1.0f;
+  const long long off = (((long long)b * p.heads + head) * p.rows_per_batch + s) * 64;
+  if (which == 2) {
+    float y[32];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) y[j] = x[c * 32 + j] * rs;
+      store_bf16x32(p.v_out + off + c * 32, y);
+    }
+    if (p.v2_out) {
+      const float mk = p.mask2[m] ? 1.0f : 0.0f;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) y[j] = x[c * 32 + j] * mk;
+        store_bf16x32(p.v2_out + off + c * 32, y);
+      }
+    }
+    return;
+  }
+  const bool rope = p.rope_cos != nullptr && s >= p.text_len;
+  const float* cosr = rope ? p.rope_cos + (long long)(s - p.text_len) * 64 : nullptr;
+  const float* sinr = rope ? p.rope_sin + (long long)(s - p.text_len) * 64 : nullptr;
+  if (which == 0) {
+    ln64_rope_store(x, rs, p.nq_w, p.nq_b, p.qk_eps, cosr, sinr, p.q_out + off);
+  } else {
+    ln64_rope_store(x, rs, p.nk_w, p.nk_b, p.qk_eps, cosr, sinr, p.k_out + off);
+    if (p.k2_out) {
+      const float mk = p.mask2[m] ? 1.0f : 0.0f;    // masked-out keys become RoPE(norm_k.bias): AP:2255, 2272, 2281
+      ln64_rope_store(x, mk, p.nk_w, p.nk_b, p.qk_eps, cosr, sinr, p.k2_out + off);
+    }
+  }
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_tiles = (p.M + BM - 1) / BM;
+  const int n_tiles = (p.N + BN - 1) / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int num_kb = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------ TMA producer ------------------------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int m_blk, n_blk;
+        tile_coords(tile, m_tiles, n_tiles, p.group_m, m_blk, n_blk);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
+          tma_load_2d(sa, &tmap_a, &full[stage], kb * BK, m_blk * BM, kEvictNormal);
+          tma_load_2d(sb, &tmap_b, &full[stage], kb * BK, n_blk * BN, kEvictLast);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer --------------------------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint64_t adesc = make_desc_sw128(sa, 1024, 0);
+          const uint64_t bdesc = make_desc_sw128(sa + A_BYTES, 1024, 0);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // +32 bytes per 16-element K step inside the 128-byte swizzle atom (descriptor address unit = 16 B)
+            mma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
+          tc_commit(&empty[stage]);   // frees the smem stage once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(&tfull[acc]);       // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------ epilogue ----------------------------------------------------
+    const int quad = warp & 3;                    // TMEM lane quadrant this warp may access
+    const int row_in_tile = quad * 32 + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      int m_blk, n_blk;
+      tile_coords(tile, m_tiles, n_tiles, p.group_m, m_blk, n_blk);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const int m = m_blk * BM + row_in_tile;
+      int b = 0, s = 0;
+      bool row_ok = m < p.M;
+      if (row_ok) {
+        b = m / p.rows_per_batch;
+        s = m - b * p.rows_per_batch;
+        if (EPI != EPI_QKV && s + p.out_row_offset < 0) row_ok = false;
+      }
+      const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(quad * 32) << 16);
+      if (EPI == EPI_QKV) {
+#pragma unroll 1
+        for (int hc = 0; hc < BN / 64; ++hc) {
+          const int n0 = n_blk * BN + hc * 64;
+          if (n0 >= p.N) break;
+          uint32_t r[64];
+          tmem_ld_x32(taddr + hc * 64, r);
+          tmem_ld_x32(taddr + hc * 64 + 32, r + 32);
+          tmem_wait_ld();
+          if (row_ok) epilogue_qkv_head(p, r, m, b, s, n0);
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          const int n0 = n_blk * BN + c * 32;
+          if (n0 >= p.N) break;
+          uint32_t r[32];
+          tmem_ld_x32(taddr + c * 32, r);
+          tmem_wait_ld();
+          if (row_ok) epilogue_cols32<EPI>(p, r, b, s, n0);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+template <int EPI>
+int launch_impl(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    VP_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    configured = true;
+  }
+  const int m_tiles = (p.M + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN;
+  const int sms = sm_count();
+  if (sms <= 0) return fail(VP_ERR_CUDA, "no CUDA device");
+  const int grid = m_tiles * n_tiles < sms ? m_tiles * n_tiles : sms;
+  gemm_bf16_kernel<EPI><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ta, tb, p);
+  VP_CHECK_CUDA(cudaGetLastError());
+  return VP_OK;
+}
+
+}  // namespace
+
+int launch_gemm(int epi, const void* A, long long lda, const void* W, long long ldw, const GemmParams& p, cudaStream_t st) {
+  VP_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, VP_ERR_BAD_SHAPE, "gemm: empty problem");
+  VP_REQUIRE(p.N % 64 == 0, VP_ERR_BAD_SHAPE, "gemm: N must be a multiple of 64");
+  VP_REQUIRE(p.K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, VP_ERR_BAD_ALIGN, "gemm: K / leading dims must be multiples of 8");
+  VP_REQUIRE(p.rows_per_batch > 0, VP_ERR_BAD_SHAPE, "gemm: rows_per_batch");
+  CUtensorMap ta, tb;
+  {
+    uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.M};
+    uint64_t str[1] = {(uint64_t)lda * 2};
+    uint32_t box[2] = {BK, BM};
+    int rc = make_tmap_bf16(&ta, A, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.N};
+    uint64_t str[1] = {(uint64_t)ldw * 2};
+    uint32_t box[2] = {BK, BN};
+    int rc = make_tmap_bf16(&tb, W, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  GemmParams q = p;
+  if (q.group_m <= 0) q.group_m = 16;
+  switch (epi) {
+    case EPI_BIAS: return launch_impl<EPI_BIAS>(ta, tb, q, st);
+    case EPI_GELU: return launch_impl<EPI_GELU>(ta, tb, q, st);
+    case EPI_RESID: return launch_impl<EPI_RESID>(ta, tb, q, st);
+    case EPI_QKV: return launch_impl<EPI_QKV>(ta, tb, q, st);
+    default: return fail(VP_ERR_UNSUPPORTED, "gemm: unknown epilogue");
+  }
+}
+
+}  // namespace vp

@@ -1,0 +1,61 @@
+// Parameter block shared by gemm.cu (kernel) and capi.cu (C ABI).
+#pragma once
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace vp {
+
+enum GemmEpilogue : int {
+  EPI_BIAS = 0,    // out = (acc + bias) * alpha
+  EPI_GELU = 1,    // out = gelu_tanh(acc + bias)                        (ATT:1200 + ACT:83)
+  EPI_RESID = 2,   // out = res + gate * (acc + bias) [+ inject]          (T3D:169-170, 181-182, 596-609)
+  EPI_QKV = 3,     // bias -> per-head LayerNorm(64) -> RoPE -> [B,H,S,64] (AP:2132-2154, 2255-2281)
+};
+
+struct GemmParams {
+  int M, N, K;
+  int group_m;               // rasterisation: m-tiles per group (L2 reuse of A)
+  // logical row m -> batch b = m / rows_per_batch, token s = m % rows_per_batch
+  int rows_per_batch;
+  // ---- plain / gelu / residual output: row (b * out_batch_rows + out_row_offset + s), skipped if s + off < 0
+  __nv_bfloat16* out;
+  long long out_batch_rows;
+  int out_row_offset;
+  int ldo;
+  const __nv_bfloat16* bias;      // [N] or null
+  float alpha;
+  // ---- residual epilogue
+  const __nv_bfloat16* res;       // row (b * res_batch_rows + res_row_offset + s), leading dim ldr
+  long long res_batch_rows;
+  int res_row_offset;
+  int ldr;
+  const float* gate;              // gate[b * gate_batch_stride + (s < text_len ? gate_text_off : gate_video_off) + n]; null -> 1
+  long long gate_batch_stride;
+  int gate_video_off, gate_text_off;
+  int text_len;
+  const __nv_bfloat16* inject;    // [B, Sv, ldi] added to video rows (s >= text_len) where inject_mask == 0
+  long long inject_batch_stride;  // elements
+  int ldi;
+  const uint8_t* inject_mask;     // [B, Sv] (1 = inside the region to synthesise -> no add) or null
+  int video_len;
+  // ---- QKV epilogue
+  int d_model;                    // H * 64
+  int heads;
+  int qkv_first;                  // 0: columns are [Q|K|V]; 1: columns are [K|V]
+  __nv_bfloat16* q_out;           // [B, H, S, 64]
+  __nv_bfloat16* k_out;
+  __nv_bfloat16* v_out;
+  __nv_bfloat16* k2_out;          // masked copy (resample processor) or null
+  __nv_bfloat16* v2_out;
+  const uint8_t* mask2;           // [M] 1 = keep
+  const float* row_scale;         // [M] multiplies (acc + bias) before the norm, or null
+  const __nv_bfloat16* nq_w; const __nv_bfloat16* nq_b;
+  const __nv_bfloat16* nk_w; const __nv_bfloat16* nk_b;
+  float qk_eps;
+  const float* rope_cos;          // [Sv, 64] fp32 or null
+  const float* rope_sin;
+};
+
+int launch_gemm(int epi, const void* A, long long lda, const void* W, long long ldw, const GemmParams& p, cudaStream_t st);
+
+}  // namespace vp

@@ -1,0 +1,92 @@
+// Host-side helpers: last-error record, TMA tensor-map encoding through the driver entry point
+// (no link-time dependency on libcuda), device properties.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/vp_b200.h"
+#include "common.cuh"
+
+namespace vp {
+
+struct ErrorState {
+  int cuda_error = 0;
+  char msg[256] = {0};
+};
+inline ErrorState& err_state() {
+  static thread_local ErrorState s;
+  return s;
+}
+inline int fail(int code, const char* what, int cuda_error = 0) {
+  ErrorState& e = err_state();
+  e.cuda_error = cuda_error;
+  snprintf(e.msg, sizeof(e.msg), "%s", what);
+  return code;
+}
+#define VP_CHECK_CUDA(expr)                                                       \
+  do {                                                                            \
+    cudaError_t _e = (expr);                                                      \
+    if (_e != cudaSuccess) return vp::fail(VP_ERR_CUDA, #expr, (int)_e);      \
+  } while (0)
+#define VP_REQUIRE(cond, code, what)              \
+  do {                                            \
+    if (!(cond)) return vp::fail((code), (what)); \
+  } while (0)
+
+typedef CUresult (*PFN_tensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                             const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                             CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                             CUtensorMapFloatOOBfill);
+
+inline PFN_tensorMapEncodeTiled encode_fn() {
+  static PFN_tensorMapEncodeTiled fn = []() -> PFN_tensorMapEncodeTiled {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess) return nullptr;
+    if (q != cudaDriverEntryPointSuccess) return nullptr;
+    return reinterpret_cast<PFN_tensorMapEncodeTiled>(f);
+  }();
+  return fn;
+}
+
+// bf16 tensor, innermost dimension contiguous, 128-byte swizzle, zero fill out of bounds.
+// dims/box are innermost-first; strides_bytes has rank-1 entries (dims 1..rank-1).
+inline int make_tmap_bf16(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims,
+                          const uint64_t* strides_bytes, const uint32_t* box) {
+  PFN_tensorMapEncodeTiled fn = encode_fn();
+  if (!fn) return fail(VP_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return fail(VP_ERR_BAD_ALIGN, "TMA base pointer not 16-byte aligned");
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[5];
+  cuuint32_t bx[5];
+  cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i > 0) {
+      gstr[i - 1] = strides_bytes[i - 1];
+      if (gstr[i - 1] % 16 != 0) return fail(VP_ERR_BAD_ALIGN, "TMA stride not a multiple of 16 bytes");
+    }
+  }
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gdim, gstr, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(VP_ERR_DRIVER, "cuTensorMapEncodeTiled failed", (int)r);
+  return VP_OK;
+}
+
+inline int sm_count() {
+  static int n = []() {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    return v;
+  }();
+  return n;
+}
+
+}  // namespace vp

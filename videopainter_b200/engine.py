@@ -1,0 +1,427 @@
+"""Host-side driver of the denoising hot path: packs a model's weights once (reference parameter names) and runs the
+branch / backbone forwards as a sequence of C-ABI kernel launches (videopainter_b200.ops).
+
+Data layout in HBM
+  residual stream   x        [B, S, D] bf16, S = text ‖ video tokens (text first: AP:2121), one buffer per layer when the
+                             caller asks for hidden_states_list (the FFN-2 epilogue writes layer i straight into slot i)
+  q, k, v (k2, v2)           [B, H, S, 64] bf16 head-major (written by the QKV GEMM epilogue, read by TMA)
+  attention output  ao       [B, S, D] bf16 token-major (A operand of the out-projection)
+  modulation tables mod      [B, 6D] fp32 per LayerNormZero (shift, scale, gate, enc_shift, enc_scale, enc_gate: NRM:376)
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import ops
+
+BF16 = torch.bfloat16
+
+
+@dataclass
+class Dims:
+    heads: int
+    head_dim: int
+    time_dim: int
+    text_dim: int
+    patch_in_channels: int      # channels seen by patch_embed.proj (32 backbone, 33 branch)
+    out_channels: int
+    patch: int
+    max_text: int
+    num_layers: int
+    eps: float = 1e-5
+    flip_sin_to_cos: bool = True
+    freq_shift: float = 0.0
+    resample: bool = False      # blocks built with CogVideoXAttnProcessor2_0_resample (T3D:98-99)
+    is_branch: bool = False
+
+    @property
+    def D(self) -> int:
+        return self.heads * self.head_dim
+
+
+@dataclass
+class PackedBlock:
+    n1_lin_w: torch.Tensor; n1_lin_b: torch.Tensor; n1_w: torch.Tensor; n1_b: torch.Tensor
+    n2_lin_w: torch.Tensor; n2_lin_b: torch.Tensor; n2_w: torch.Tensor; n2_b: torch.Tensor
+    qkv_w: torch.Tensor; qkv_b: torch.Tensor
+    nq_w: torch.Tensor; nq_b: torch.Tensor; nk_w: torch.Tensor; nk_b: torch.Tensor
+    out_w: torch.Tensor; out_b: torch.Tensor
+    ff1_w: torch.Tensor; ff1_b: torch.Tensor; ff2_w: torch.Tensor; ff2_b: torch.Tensor
+
+
+@dataclass
+class PackedModel:
+    dims: Dims
+    blocks: List[PackedBlock]
+    patch_w: torch.Tensor; patch_b: torch.Tensor; kpad: int
+    text_w: torch.Tensor; text_b: torch.Tensor
+    pos: torch.Tensor
+    t1_w: torch.Tensor; t1_b: torch.Tensor; t2_w: torch.Tensor; t2_b: torch.Tensor
+    nf_w: Optional[torch.Tensor] = None; nf_b: Optional[torch.Tensor] = None
+    no_lin_w: Optional[torch.Tensor] = None; no_lin_b: Optional[torch.Tensor] = None
+    no_w: Optional[torch.Tensor] = None; no_b: Optional[torch.Tensor] = None
+    proj_w: Optional[torch.Tensor] = None; proj_b: Optional[torch.Tensor] = None
+    branch_w: List[torch.Tensor] = field(default_factory=list)
+    branch_b: List[torch.Tensor] = field(default_factory=list)
+    workspace: Dict[Any, Any] = field(default_factory=dict)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# weight packing
+# ------------------------------------------------------------------------------------------------------------------
+def _linear_from_sd(sd: Dict[str, torch.Tensor], prefix: str, lora_scale: float = 1.0):
+    """Plain nn.Linear or a PEFT lora.Linear (base_layer + lora_A/lora_B per adapter); the adapter is merged:
+    W' = W + scale * B @ A with alpha == r at inference."""
+    if prefix + ".weight" in sd:
+        return sd[prefix + ".weight"], sd.get(prefix + ".bias")
+    w = sd[prefix + ".base_layer.weight"].float()
+    b = sd.get(prefix + ".base_layer.bias")
+    for key in sd:
+        if key.startswith(prefix + ".lora_A.") and key.endswith(".weight"):
+            a = sd[key].float()
+            bb = sd[key.replace(".lora_A.", ".lora_B.")].float()
+            w = w + lora_scale * (bb.to(w.device) @ a.to(w.device))
+    return w, b
+
+
+def pack_state_dict(sd: Dict[str, torch.Tensor], dims: Dims, device, lora_scale: float = 1.0) -> PackedModel:
+    def t(x):
+        return None if x is None else x.detach().to(device=device, dtype=BF16).contiguous()
+
+    def lin(prefix):
+        w, b = _linear_from_sd(sd, prefix, lora_scale)
+        return t(w), t(b)
+
+    D = dims.D
+    blocks = []
+    for i in range(dims.num_layers):
+        p = f"transformer_blocks.{i}."
+        wq, bq = lin(p + "attn1.to_q")
+        wk, bk = lin(p + "attn1.to_k")
+        wv, bv = lin(p + "attn1.to_v")
+        if bq is None or bk is None or bv is None:
+            raise ValueError("attention projections without bias are not supported (CogVideoX uses attention_bias=True)")
+        n1w, n1b = lin(p + "norm1.linear")
+        n2w, n2b = lin(p + "norm2.linear")
+        ow, ob = lin(p + "attn1.to_out.0")
+        f1w, f1b = lin(p + "ff.net.0.proj")
+        f2w, f2b = lin(p + "ff.net.2")
+        blocks.append(PackedBlock(
+            n1_lin_w=n1w, n1_lin_b=n1b, n1_w=t(sd[p + "norm1.norm.weight"]), n1_b=t(sd[p + "norm1.norm.bias"]),
+            n2_lin_w=n2w, n2_lin_b=n2b, n2_w=t(sd[p + "norm2.norm.weight"]), n2_b=t(sd[p + "norm2.norm.bias"]),
+            qkv_w=torch.cat([wq, wk, wv], dim=0).contiguous(), qkv_b=torch.cat([bq, bk, bv], dim=0).contiguous(),
+            nq_w=t(sd[p + "attn1.norm_q.weight"]), nq_b=t(sd[p + "attn1.norm_q.bias"]),
+            nk_w=t(sd[p + "attn1.norm_k.weight"]), nk_b=t(sd[p + "attn1.norm_k.bias"]),
+            out_w=ow, out_b=ob, ff1_w=f1w, ff1_b=f1b, ff2_w=f2w, ff2_b=f2b))
+    conv = sd["patch_embed.proj.weight"]                                  # [D, C, p, p] -> [D, C*p*p], zero-padded to 64
+    k = conv.shape[1] * conv.shape[2] * conv.shape[3]
+    kpad = (k + 63) // 64 * 64
+    pw = torch.zeros(D, kpad, dtype=BF16, device=device)
+    pw[:, :k] = conv.detach().reshape(D, k).to(device=device, dtype=BF16)
+    tw, tb = lin("patch_embed.text_proj")
+    if "patch_embed.pos_embedding" not in sd:
+        raise ValueError("only the CogVideoX-5B family (rotary + learned positional table) is supported")
+    t1w, t1b = lin("time_embedding.linear_1")
+    t2w, t2b = lin("time_embedding.linear_2")
+    pm = PackedModel(dims=dims, blocks=blocks, patch_w=pw, patch_b=t(sd["patch_embed.proj.bias"]), kpad=kpad,
+                     text_w=tw, text_b=tb, pos=t(sd["patch_embed.pos_embedding"][0]),
+                     t1_w=t1w, t1_b=t1b, t2_w=t2w, t2_b=t2b)
+    if dims.is_branch:
+        for i in range(dims.num_layers):
+            w, b = lin(f"branch_blocks.{i}")
+            pm.branch_w.append(w)
+            pm.branch_b.append(b)
+    else:
+        pm.nf_w, pm.nf_b = t(sd["norm_final.weight"]), t(sd["norm_final.bias"])
+        pm.no_lin_w, pm.no_lin_b = lin("norm_out.linear")
+        pm.no_w, pm.no_b = t(sd["norm_out.norm.weight"]), t(sd["norm_out.norm.bias"])
+        pm.proj_w, pm.proj_b = lin("proj_out")
+    return pm
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# workspace
+# ------------------------------------------------------------------------------------------------------------------
+class _Workspace:
+    def __init__(self, pm: PackedModel, B: int, S: int, Sv: int, device):
+        D, H = pm.dims.D, pm.dims.heads
+        e = lambda *shape, dtype=BF16: torch.empty(*shape, dtype=dtype, device=device)   # noqa: E731
+        self.xn = e(B * S, D)
+        self.q = e(B, H, S, 64)
+        self.k = e(B, H, S, 64)
+        self.v = e(B, H, S, 64)
+        self.k2 = None
+        self.v2 = None
+        self.ao = e(B * S, D)
+        self.xmid = e(B, S, D)
+        self.ffm = e(B * S, 4 * D)
+        self.mod1 = e(B, 6 * D, dtype=torch.float32)
+        self.mod2 = e(B, 6 * D, dtype=torch.float32)
+        self.patches = e(B * Sv, pm.kpad)
+        self.ping = [None, None]
+        self.device = device
+        self.shape = (B, H, S)
+
+    def second_kv(self):
+        if self.k2 is None:
+            B, H, S = self.shape
+            self.k2 = torch.empty(B, H, S, 64, dtype=BF16, device=self.device)
+            self.v2 = torch.empty(B, H, S, 64, dtype=BF16, device=self.device)
+        return self.k2, self.v2
+
+
+def _workspace(pm: PackedModel, B, S, Sv, device) -> _Workspace:
+    key = (B, S, Sv, str(device))
+    ws = pm.workspace.get(key)
+    if ws is None:
+        pm.workspace.clear()
+        ws = _Workspace(pm, B, S, Sv, device)
+        pm.workspace[key] = ws
+    return ws
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# forward pieces
+# ------------------------------------------------------------------------------------------------------------------
+def _time_embedding(pm: PackedModel, timestep: torch.Tensor, B: int, device) -> torch.Tensor:
+    d = pm.dims
+    if not torch.is_tensor(timestep):
+        timestep = torch.tensor([timestep], device=device)
+    timestep = timestep.to(device)
+    if timestep.ndim == 0:
+        timestep = timestep[None]
+    if timestep.shape[0] != B:
+        timestep = timestep.expand(B)
+    timestep = timestep.contiguous()
+    if timestep.dtype not in (torch.int64, torch.float32):
+        timestep = timestep.to(torch.int64 if not timestep.is_floating_point() else torch.float32)
+    sin = ops.time_sinusoid(timestep, d.D, d.flip_sin_to_cos, d.freq_shift)       # EMB:27-78
+    h = ops.gemv(sin, pm.t1_w, pm.t1_b, act_silu=False)                            # EMB:765
+    return ops.gemv(h, pm.t2_w, pm.t2_b, act_silu=True)                            # EMB:768-770
+
+
+def _embed(pm: PackedModel, ws: _Workspace, x: torch.Tensor, text: torch.Tensor, src0: torch.Tensor,
+           src1: Optional[torch.Tensor], B, Fr, H, W, St, Sv):
+    """CogVideoXPatchEmbed.forward EMB:400-454 into the joint residual stream x [B, S, D]."""
+    d = pm.dims
+    S = St + Sv
+    D = d.D
+    ops.patchify(src0, src1, ws.patches, B * Fr, H, W, pm.kpad)
+    # video rows: conv-as-GEMM + bias + positional table rows [St, S)
+    ops.gemm_gate_residual(ws.patches, pm.patch_w, pm.patch_b, x, B * Sv, D, pm.kpad, rows_per_batch=Sv, out_batch_rows=S,
+                           out_row_offset=St, res=pm.pos, res_batch_rows=0, res_row_offset=St)
+    # text rows: text_proj + positional table rows [0, St)
+    ops.gemm_gate_residual(text, pm.text_w, pm.text_b, x, B * St, D, d.text_dim, rows_per_batch=St, out_batch_rows=S,
+                           out_row_offset=0, res=pm.pos, res_batch_rows=0, res_row_offset=0)
+
+
+def _block(pm: PackedModel, blk: PackedBlock, ws: _Workspace, x_in: torch.Tensor, x_out: torch.Tensor, emb: torch.Tensor,
+           rope, B, S, St, Sv, resample_mask_u8=None, prev=None, prev_w=None, prev_mask=None, inject=None, inject_mask=None):
+    """CogVideoXBlock.forward T3D:125-184 (+ branch injection T3D:596-609 fused into the FFN-2 epilogue)."""
+    d = pm.dims
+    D, H = d.D, d.heads
+    M = B * S
+    OFF1 = (0, D, 3 * D, 4 * D)       # shift, scale (video) / enc_shift, enc_scale (text) inside the 6D table
+    ops.gemv(emb, blk.n1_lin_w, blk.n1_lin_b, act_silu=True, out=ws.mod1)
+    ops.ln_modulate(x_in, S, 0, ws.xn, B, S, D, blk.n1_w, blk.n1_b, d.eps, ws.mod1, OFF1, St)
+    use_prev = prev is not None and prev_w is not None and prev_w > 0.0
+    scale = 1.0 / math.sqrt(d.head_dim)
+    if d.resample and not use_prev:                                   # AP:2255-2256: masked copy of own K/V
+        k2, v2 = ws.second_kv()
+        ops.gemm_qkv(ws.xn, blk.qkv_w, blk.qkv_b, M, D, S, H, 0, ws.q, ws.k, ws.v, (blk.nq_w, blk.nq_b), (blk.nk_w, blk.nk_b),
+                     1e-6, rope, St, k2_out=k2, v2_out=v2, mask2=resample_mask_u8)
+        ops.attention(ws.q, ws.k, ws.v, ws.ao, B, H, S, S, scale, k1=k2, v1=v2, kv_len1=S)
+    else:
+        ops.gemm_qkv(ws.xn, blk.qkv_w, blk.qkv_b, M, D, S, H, 0, ws.q, ws.k, ws.v, (blk.nq_w, blk.nq_b), (blk.nk_w, blk.nk_b),
+                     1e-6, rope, St, )
+        if use_prev:
+            # T3D:141-146: norm1 of the previous window's states with the current timestep embedding
+            k2, v2 = ws.second_kv()
+            ops.ln_modulate(prev, S, 0, ws.xn, B, S, D, blk.n1_w, blk.n1_b, d.eps, ws.mod1, OFF1, St)
+            kv_w = blk.qkv_w[D:]
+            kv_b = blk.qkv_b[D:]
+            if d.resample:                                            # AP:2247-2252, one softmax over 2S keys
+                ops.gemm_qkv(ws.xn, kv_w, kv_b, M, D, S, H, 1, None, k2, v2, None, (blk.nk_w, blk.nk_b), 1e-6, rope, St,
+                             row_scale=prev_mask)
+                ops.attention(ws.q, ws.k, ws.v, ws.ao, B, H, S, S, scale, k1=k2, v1=v2, kv_len1=S)
+            else:                                                     # AP:2156-2189, blend of two attentions
+                ops.gemm_qkv(ws.xn, kv_w, kv_b, M, D, S, H, 1, None, k2, v2, None, (blk.nk_w, blk.nk_b), 1e-6, rope, St)
+                ops.attention(ws.q, ws.k, ws.v, ws.ao, B, H, S, S, scale, out_scale=1.0 - prev_w)
+                ops.attention(ws.q, k2, v2, ws.ao, B, H, S, S, scale, out_scale=prev_w, accumulate=True)
+        else:
+            ops.attention(ws.q, ws.k, ws.v, ws.ao, B, H, S, S, scale)
+    # to_out + gated residual (AP:2202, T3D:169-170): gate = chunk 2 (video) / 5 (text)
+    ops.gemm_gate_residual(ws.ao, blk.out_w, blk.out_b, ws.xmid, M, D, D, rows_per_batch=S, out_batch_rows=S, out_row_offset=0,
+                           res=x_in, res_batch_rows=S, res_row_offset=0, gate=ws.mod1, gate_video_off=2 * D,
+                           gate_text_off=5 * D, text_len=St)
+    ops.gemv(emb, blk.n2_lin_w, blk.n2_lin_b, act_silu=True, out=ws.mod2)
+    ops.ln_modulate(ws.xmid, S, 0, ws.xn, B, S, D, blk.n2_w, blk.n2_b, d.eps, ws.mod2, OFF1, St)
+    ops.gemm_gelu(ws.xn, blk.ff1_w, blk.ff1_b, ws.ffm, M, 4 * D, D)
+    inj_kw = {}
+    if inject is not None:
+        inj_kw = dict(inject=inject, inject_batch_stride=inject.stride(0), ldi=inject.stride(1), inject_mask=inject_mask,
+                      video_len=Sv)
+    ops.gemm_gate_residual(ws.ffm, blk.ff2_w, blk.ff2_b, x_out, M, D, 4 * D, rows_per_batch=S, out_batch_rows=S, out_row_offset=0,
+                           res=ws.xmid, res_batch_rows=S, res_row_offset=0, gate=ws.mod2, gate_video_off=2 * D,
+                           gate_text_off=5 * D, text_len=St, **inj_kw)
+
+
+def _prep_rope(rope, device, Sv):
+    if rope is None:
+        return None
+    cos, sin = rope
+    cos = cos.to(device=device, dtype=torch.float32).contiguous()
+    sin = sin.to(device=device, dtype=torch.float32).contiguous()
+    if cos.shape != (Sv, 64) or sin.shape != (Sv, 64):
+        raise ValueError(f"image_rotary_emb must be two [{Sv}, 64] tables, got {tuple(cos.shape)}")
+    return cos, sin
+
+
+def _check_inputs(pm: PackedModel, hidden_states, encoder_hidden_states):
+    if hidden_states.ndim != 5:
+        raise ValueError("hidden_states must be [batch, frames, channels, height, width]")
+    if not hidden_states.is_cuda:
+        raise RuntimeError("videopainter_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
+    d = pm.dims
+    if encoder_hidden_states.shape[1] != d.max_text or encoder_hidden_states.shape[2] != d.text_dim:
+        raise ValueError(f"encoder_hidden_states must be [B, {d.max_text}, {d.text_dim}]")
+
+
+@torch.no_grad()
+def branch_forward(pm: PackedModel, hidden_states: torch.Tensor, encoder_hidden_states: torch.Tensor, branch_cond: torch.Tensor,
+                   timestep, image_rotary_emb, conditioning_scale: float = 1.0) -> List[torch.Tensor]:
+    """CogvideoXBranchModel.forward BR:295-434 (wo_text = False)."""
+    _check_inputs(pm, hidden_states, encoder_hidden_states)
+    d = pm.dims
+    dtype = hidden_states.dtype
+    dev = hidden_states.device
+    B, Fr, C, H, W = hidden_states.shape
+    if C + branch_cond.shape[2] != d.patch_in_channels:
+        raise ValueError(f"branch expects {d.patch_in_channels} conditioning channels, got {C} + {branch_cond.shape[2]}")
+    Sv = Fr * (H // d.patch) * (W // d.patch)
+    St = encoder_hidden_states.shape[1]
+    S = St + Sv
+    if pm.pos.shape[0] != S:
+        raise ValueError("resolution / frame count must match the learned positional table (EMB:433-437)")
+    ws = _workspace(pm, B, S, Sv, dev)
+    emb = _time_embedding(pm, timestep, B, dev)
+    rope = _prep_rope(image_rotary_emb, dev, Sv)
+    x = [torch.empty(B, S, d.D, dtype=BF16, device=dev) for _ in range(d.num_layers + 1)]
+    _embed(pm, ws, x[0], encoder_hidden_states.to(BF16).contiguous(), hidden_states.to(BF16).contiguous(),
+           branch_cond.to(BF16).contiguous(), B, Fr, H, W, St, Sv)
+    outs = []
+    for i, blk in enumerate(pm.blocks):
+        _block(pm, blk, ws, x[i], x[i + 1], emb, rope, B, S, St, Sv)
+    for i in range(d.num_layers):
+        o = torch.empty(B, Sv, d.D, dtype=BF16, device=dev)
+        # branch_blocks[i] on the video rows only (BR:416-421); text rows are dropped by the negative row offset
+        ops.gemm_bias(x[i + 1], pm.branch_w[i], pm.branch_b[i], o, B * S, d.D, d.D, rows_per_batch=S, out_batch_rows=Sv,
+                      out_row_offset=-St, alpha=float(conditioning_scale))
+        outs.append(o.to(dtype))
+    return outs
+
+
+@torch.no_grad()
+def transformer_forward(pm: PackedModel, hidden_states: torch.Tensor, encoder_hidden_states: torch.Tensor, timestep,
+                        image_rotary_emb=None, attention_kwargs: Optional[Dict[str, Any]] = None,
+                        branch_block_samples: Optional[Sequence[torch.Tensor]] = None,
+                        branch_block_masks: Optional[torch.Tensor] = None, add_first: bool = False,
+                        return_hidden_states: bool = False, return_resample_mask: bool = False,
+                        id_pool_resample_learnable: bool = False):
+    """CogVideoXTransformer3DModel.forward T3D:472-646; returns (output, hidden_states_list | None, resample_mask | None)."""
+    _check_inputs(pm, hidden_states, encoder_hidden_states)
+    d = pm.dims
+    dtype = hidden_states.dtype
+    dev = hidden_states.device
+    B, Fr, C, H, W = hidden_states.shape
+    if C != d.patch_in_channels:
+        raise ValueError(f"transformer expects {d.patch_in_channels} latent channels, got {C}")
+    Sv = Fr * (H // d.patch) * (W // d.patch)
+    St = encoder_hidden_states.shape[1]
+    S = St + Sv
+    D = d.D
+    if pm.pos.shape[0] != S:
+        raise ValueError("resolution / frame count must match the learned positional table (EMB:433-437)")
+    L = d.num_layers
+    ws = _workspace(pm, B, S, Sv, dev)
+    emb = _time_embedding(pm, timestep, B, dev)
+    rope = _prep_rope(image_rotary_emb, dev, Sv)
+
+    mask_u8 = None
+    if branch_block_masks is not None:
+        mask_u8 = torch.empty(B, Sv, dtype=torch.uint8, device=dev)
+        ops.mask_pool(branch_block_masks.to(BF16).contiguous(), mask_u8, B * Fr, H, W)
+    resample_mask = None
+    rm_u8 = None
+    if id_pool_resample_learnable or return_resample_mask:
+        if mask_u8 is None:
+            raise ValueError("id_pool_resample needs masks")                      # T3D:536-537
+        rm_u8 = torch.zeros(B, S, dtype=torch.uint8, device=dev)
+        rm_u8[:, St:] = mask_u8
+        resample_mask = rm_u8.bool()
+    if d.resample and rm_u8 is None:
+        raise ValueError("the ID-resample attention processor needs branch_block_masks (T3D:534-543)")
+
+    kw = dict(attention_kwargs) if attention_kwargs else {}
+    kw.pop("scale", None)      # LoRA scale: adapters are merged at pack time
+    prev_states = kw.get("prev_hidden_states")
+    prev_w = kw.get("prev_clip_weight")
+    prev_mask_f = None
+    if prev_states is not None and d.resample and prev_w is not None and prev_w > 0.0:
+        pmk = kw.get("prev_resample_mask")
+        if pmk is None:
+            raise ValueError("prev_resample_mask is required with prev_hidden_states on the ID-resample processor")
+        prev_mask_f = (pmk.to(device=dev, dtype=torch.float32) * float(prev_w)).reshape(-1).contiguous()
+
+    if return_hidden_states:
+        arena = torch.empty(L + 1, B, S, D, dtype=BF16, device=dev)
+        xs = [arena[i] for i in range(L + 1)]
+    else:
+        if ws.ping[0] is None:
+            ws.ping = [torch.empty(B, S, D, dtype=BF16, device=dev) for _ in range(2)]
+        xs = [ws.ping[i % 2] for i in range(L + 1)]
+
+    _embed(pm, ws, xs[0], encoder_hidden_states.to(BF16).contiguous(), hidden_states.to(BF16).contiguous(), None,
+           B, Fr, H, W, St, Sv)
+
+    samples = None
+    if branch_block_samples is not None:
+        samples = []
+        for s in branch_block_samples:
+            s = s.to(BF16)
+            if s.stride(-1) != 1 or s.shape != (B, Sv, D):
+                s = s.contiguous()
+            samples.append(s)
+    interval = int(math.ceil(L / len(samples))) if samples else 1                  # T3D:598-599
+
+    for i, blk in enumerate(pm.blocks):
+        inject = None
+        if samples is not None:
+            if not add_first:
+                inject = samples[i // interval]
+            elif i < len(samples):
+                inject = samples[i]
+        prev = None
+        if prev_states is not None:
+            prev = prev_states.get(i)                                              # T3D:574-582
+            if prev is not None:
+                prev = prev.to(device=dev, dtype=BF16).contiguous()
+        _block(pm, blk, ws, xs[i], xs[i + 1], emb, rope, B, S, St, Sv, resample_mask_u8=None if rm_u8 is None else rm_u8.reshape(-1),
+               prev=prev, prev_w=prev_w if prev is not None else None, prev_mask=prev_mask_f, inject=inject,
+               inject_mask=mask_u8 if inject is not None else None)
+
+    # final head T3D:613-632
+    mod = ops.gemv(emb, pm.no_lin_w, pm.no_lin_b, act_silu=True)                   # [B, 2D]: shift | scale (NRM:78)
+    xf = ws.xn[: B * Sv]
+    ops.ln_final(xs[L], S, St, xf, B, Sv, D, pm.nf_w, pm.nf_b, pm.no_w, pm.no_b, d.eps, mod, 0, D)
+    n_out = d.patch * d.patch * d.out_channels
+    po = ws.ao.view(-1)[: B * Sv * n_out].view(B * Sv, n_out)
+    ops.gemm_bias(xf, pm.proj_w, pm.proj_b, po, B * Sv, n_out, D, rows_per_batch=B * Sv, out_batch_rows=0, out_row_offset=0)
+    out = torch.empty(B, Fr, d.out_channels, H, W, dtype=BF16, device=dev)
+    ops.unpatchify(po, out, B * Fr, d.out_channels, H, W)
+    hs_list = [xs[i + 1] for i in range(L)] if return_hidden_states else None
+    return out.to(dtype), hs_list, resample_mask

@@ -1,0 +1,324 @@
+"""Host-side mirror of the reference's plugin interface for the denoising path.
+
+Two ways in, one engine (videopainter_b200.engine):
+
+* `CogVideoXTransformer3DModel` / `CogvideoXBranchModel` below have the reference's constructor arguments, parameter
+  names (so `load_state_dict` of a reference checkpoint works) and `forward` signatures (T3D:472-489, BR:295-309),
+  and run entirely on the B200 kernels.
+* `install()` patches the `forward` of the reference's own two classes (when the diffusers fork is importable), so
+  `infer/inpaint.py`, `infer/edit.py` and the pipelines run unchanged on top of the new path.
+
+Neither has a CPU / eager fallback: a forward on a non-CUDA tensor raises.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Any, Dict, List, Optional, Tuple, Union
+
+import torch
+import torch.nn as nn
+
+from . import engine
+from .engine import Dims
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# parameter containers with the reference's names (SURVEY.md §8a "State-dict layout")
+# ------------------------------------------------------------------------------------------------------------------
+class _LayerNormZero(nn.Module):           # NRM:358-372
+    def __init__(self, cond_dim, dim, eps, **fk):
+        super().__init__()
+        self.linear = nn.Linear(cond_dim, 6 * dim, **fk)
+        self.norm = nn.LayerNorm(dim, eps=eps, **fk)
+
+
+class _AdaLayerNorm(nn.Module):            # NRM:44-65
+    def __init__(self, cond_dim, dim, eps, **fk):
+        super().__init__()
+        self.linear = nn.Linear(cond_dim, 2 * dim, **fk)
+        self.norm = nn.LayerNorm(dim, eps=eps, **fk)
+
+
+class _Attention(nn.Module):               # AP:41-264 (the parts CogVideoX uses)
+    def __init__(self, dim, heads, head_dim, **fk):
+        super().__init__()
+        self.heads = heads
+        self.to_q = nn.Linear(dim, dim, **fk)
+        self.to_k = nn.Linear(dim, dim, **fk)
+        self.to_v = nn.Linear(dim, dim, **fk)
+        self.to_out = nn.ModuleList([nn.Linear(dim, dim, **fk), nn.Dropout(0.0)])
+        self.norm_q = nn.LayerNorm(head_dim, eps=1e-6, **fk)
+        self.norm_k = nn.LayerNorm(head_dim, eps=1e-6, **fk)
+
+
+class _GELUProj(nn.Module):                # ACT:65-90
+    def __init__(self, dim, inner, **fk):
+        super().__init__()
+        self.proj = nn.Linear(dim, inner, **fk)
+
+
+class _FeedForward(nn.Module):             # ATT:1144-1195
+    def __init__(self, dim, **fk):
+        super().__init__()
+        self.net = nn.ModuleList([_GELUProj(dim, 4 * dim, **fk), nn.Dropout(0.0), nn.Linear(4 * dim, dim, **fk), nn.Dropout(0.0)])
+
+
+class CogVideoXAttnProcessor2_0:           # selector objects only: the maths lives in the kernels
+    pass
+
+
+class CogVideoXAttnProcessor2_0_resample:
+    pass
+
+
+class CogVideoXBlock(nn.Module):           # T3D:38-123
+    def __init__(self, dim, heads, head_dim, time_dim, eps, resample, **fk):
+        super().__init__()
+        self.norm1 = _LayerNormZero(time_dim, dim, eps, **fk)
+        self.processor = CogVideoXAttnProcessor2_0_resample() if resample else CogVideoXAttnProcessor2_0()
+        self.attn1 = _Attention(dim, heads, head_dim, **fk)
+        self.norm2 = _LayerNormZero(time_dim, dim, eps, **fk)
+        self.ff = _FeedForward(dim, **fk)
+
+
+class _PatchEmbed(nn.Module):              # EMB:337-398
+    def __init__(self, patch, in_ch, dim, text_dim, n_tokens, max_text, **fk):
+        super().__init__()
+        self.patch_size = patch
+        self.max_text_seq_length = max_text
+        self.proj = nn.Conv2d(in_ch, dim, kernel_size=(patch, patch), stride=patch, **fk)
+        self.text_proj = nn.Linear(text_dim, dim, **fk)
+        self.register_buffer("pos_embedding", torch.zeros(1, n_tokens, dim, **fk), persistent=True)
+
+
+class _TimestepEmbedding(nn.Module):       # EMB:729-760
+    def __init__(self, dim, time_dim, **fk):
+        super().__init__()
+        self.linear_1 = nn.Linear(dim, time_dim, **fk)
+        self.linear_2 = nn.Linear(time_dim, time_dim, **fk)
+
+
+class _Timesteps(nn.Module):               # EMB:777-793
+    def __init__(self, flip_sin_to_cos, freq_shift):
+        super().__init__()
+        self.flip_sin_to_cos = flip_sin_to_cos
+        self.downscale_freq_shift = freq_shift
+
+
+@dataclass
+class Transformer2DModelOutput:
+    sample: torch.Tensor
+
+
+@dataclass
+class CogvideoxBranchOutput:
+    branch_block_samples: Optional[List[torch.Tensor]]
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# live-module introspection (works on the mirror classes and on the reference's classes alike)
+# ------------------------------------------------------------------------------------------------------------------
+def _base(linear):
+    return getattr(linear, "base_layer", linear)          # PEFT lora.Linear wraps the original module
+
+
+def dims_from_module(m: nn.Module, is_branch: bool) -> Dims:
+    blocks = m.transformer_blocks                           # never config["num_layers"] (BR:265-269 mutates it)
+    a0 = blocks[0].attn1
+    heads = int(a0.heads)
+    dim = _base(a0.to_q).out_features
+    pe = m.patch_embed
+    p = int(pe.patch_size)
+    return Dims(heads=heads, head_dim=dim // heads, time_dim=m.time_embedding.linear_2.out_features,
+                text_dim=pe.text_proj.in_features, patch_in_channels=pe.proj.in_channels,
+                out_channels=m.proj_out.out_features // (p * p), patch=p, max_text=int(pe.max_text_seq_length),
+                num_layers=len(blocks), eps=float(m.norm_final.eps), flip_sin_to_cos=bool(m.time_proj.flip_sin_to_cos),
+                freq_shift=float(m.time_proj.downscale_freq_shift),
+                resample=type(blocks[0].processor).__name__ == "CogVideoXAttnProcessor2_0_resample",
+                is_branch=is_branch)
+
+
+def _fingerprint(m: nn.Module):
+    fp = []
+    for p in m.parameters():
+        fp.append((p.data_ptr(), p._version))
+    return (len(fp), hash(tuple(fp)))
+
+
+def packed_for(m: nn.Module, is_branch: bool, device) -> engine.PackedModel:
+    """Packed-weight cache keyed on (data_ptr, version) of every parameter: rebuilt after .to(), LoRA load, training."""
+    fp = (_fingerprint(m), str(device))
+    cached = getattr(m, "_vp_packed", None)
+    if cached is not None and cached[0] == fp:
+        return cached[1]
+    dims = dims_from_module(m, is_branch)
+    if dims.head_dim != 64:
+        raise ValueError("videopainter_b200 supports attention_head_dim == 64 (CogVideoX) only")
+    pm = engine.pack_state_dict(m.state_dict(), dims, device)
+    object.__setattr__(m, "_vp_packed", (fp, pm))
+    return pm
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# forwards with the reference signatures
+# ------------------------------------------------------------------------------------------------------------------
+def transformer_forward(self, hidden_states: torch.Tensor, encoder_hidden_states: torch.Tensor,
+                        timestep: Union[int, float, torch.LongTensor], timestep_cond: Optional[torch.Tensor] = None,
+                        image_rotary_emb: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+                        attention_kwargs: Optional[Dict[str, Any]] = None,
+                        branch_block_samples: Optional[torch.Tensor] = None,
+                        branch_block_masks: Optional[torch.Tensor] = None, add_first: Optional[bool] = False,
+                        self_guidance_hidden_states: Optional[torch.Tensor] = None,
+                        self_guidance_masks: Optional[torch.Tensor] = None,
+                        return_hidden_states: Optional[bool] = False, return_resample_mask: Optional[bool] = False,
+                        id_pool_resample_learnable: Optional[bool] = False, return_dict: bool = True):
+    """Drop-in for CogVideoXTransformer3DModel.forward (T3D:472-646)."""
+    if timestep_cond is not None:
+        raise NotImplementedError("timestep_cond is not used by any CogVideoX checkpoint (cond_proj is None, EMB:744-747)")
+    if self_guidance_hidden_states is not None or self_guidance_masks is not None:
+        raise NotImplementedError("self-guidance (T3D:593-594) is not used by the VideoPainter pipelines")
+    pm = packed_for(self, False, hidden_states.device)
+    out, hs, rmask = engine.transformer_forward(
+        pm, hidden_states, encoder_hidden_states, timestep, image_rotary_emb, attention_kwargs, branch_block_samples,
+        branch_block_masks, bool(add_first), bool(return_hidden_states), bool(return_resample_mask),
+        bool(id_pool_resample_learnable))
+    if not return_dict:                                      # T3D:638-645
+        if return_hidden_states:
+            return (out, hs, rmask) if return_resample_mask else (out, hs)
+        return (out,)
+    return _output_class("Transformer2DModelOutput", Transformer2DModelOutput)(sample=out)
+
+
+def branch_forward(self, hidden_states: torch.Tensor, encoder_hidden_states: torch.Tensor = None,
+                   branch_cond: torch.Tensor = None, branch_mode: torch.Tensor = None, conditioning_scale: float = 1.0,
+                   timestep: Union[int, float, torch.LongTensor] = None, timestep_cond: Optional[torch.Tensor] = None,
+                   image_rotary_emb: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+                   attention_kwargs: Optional[Dict[str, Any]] = None, mask_add: Optional[bool] = False,
+                   wo_text: Optional[bool] = False, return_dict: bool = True):
+    """Drop-in for CogvideoXBranchModel.forward (BR:295-434)."""
+    if wo_text:
+        raise NotImplementedError("wo_text branch (BR:407-412) is not enabled by any shipped script")
+    if timestep_cond is not None:
+        raise NotImplementedError("timestep_cond is not used by any CogVideoX checkpoint")
+    pm = packed_for(self, True, hidden_states.device)
+    samples = engine.branch_forward(pm, hidden_states, encoder_hidden_states, branch_cond, timestep, image_rotary_emb,
+                                    conditioning_scale)
+    samples = None if len(samples) == 0 else samples
+    if not return_dict:
+        return (samples,)
+    return _output_class("CogvideoxBranchOutput", CogvideoxBranchOutput)(branch_block_samples=samples)
+
+
+_REF_OUTPUTS: Dict[str, Any] = {}
+
+
+def _output_class(name, default):
+    return _REF_OUTPUTS.get(name, default)
+
+
+class _Base(nn.Module):
+    def _build(self, is_branch: bool, num_attention_heads, attention_head_dim, in_channels, out_channels, flip_sin_to_cos,
+               freq_shift, time_embed_dim, text_embed_dim, num_layers, sample_width, sample_height, sample_frames,
+               patch_size, temporal_compression_ratio, max_text_seq_length, norm_eps, use_rotary_positional_embeddings,
+               use_learned_positional_embeddings, id_pool_resample_learnable, fk):
+        if not (use_rotary_positional_embeddings and use_learned_positional_embeddings):
+            raise ValueError("only rotary + learned positional embeddings (CogVideoX-5B-I2V) are supported")
+        dim = num_attention_heads * attention_head_dim
+        frames = (sample_frames - 1) // temporal_compression_ratio + 1
+        n_tokens = max_text_seq_length + frames * (sample_height // patch_size) * (sample_width // patch_size)
+        cin = in_channels
+        if is_branch:
+            cin = in_channels * 2 + 1 if in_channels == 16 else in_channels + 1                  # BR:90
+        self.patch_embed = _PatchEmbed(patch_size, cin, dim, text_embed_dim, n_tokens, max_text_seq_length, **fk)
+        self.time_proj = _Timesteps(flip_sin_to_cos, freq_shift)
+        self.time_embedding = _TimestepEmbedding(dim, time_embed_dim, **fk)
+        self.transformer_blocks = nn.ModuleList([
+            CogVideoXBlock(dim, num_attention_heads, attention_head_dim, time_embed_dim, norm_eps,
+                           id_pool_resample_learnable and not is_branch, **fk) for _ in range(num_layers)])
+        self.norm_final = nn.LayerNorm(dim, norm_eps, **fk)
+        self.norm_out = _AdaLayerNorm(time_embed_dim, dim, norm_eps, **fk)
+        self.proj_out = nn.Linear(dim, patch_size * patch_size * out_channels, **fk)
+        if is_branch:
+            self.branch_blocks = nn.ModuleList([nn.Linear(dim, dim, **fk) for _ in range(num_layers)])
+            self.branch_x_embedder = nn.Linear(in_channels, dim, **fk)
+
+
+class CogVideoXTransformer3DModel(_Base):
+    """Same constructor arguments as the reference class (T3D:275-303); extra `device` / `dtype` factory kwargs."""
+
+    def __init__(self, num_attention_heads: int = 30, attention_head_dim: int = 64, in_channels: int = 16,
+                 out_channels: Optional[int] = 16, flip_sin_to_cos: bool = True, freq_shift: int = 0,
+                 time_embed_dim: int = 512, text_embed_dim: int = 4096, num_layers: int = 30, dropout: float = 0.0,
+                 attention_bias: bool = True, sample_width: int = 90, sample_height: int = 60, sample_frames: int = 49,
+                 patch_size: int = 2, temporal_compression_ratio: int = 4, max_text_seq_length: int = 226,
+                 activation_fn: str = "gelu-approximate", timestep_activation_fn: str = "silu",
+                 norm_elementwise_affine: bool = True, norm_eps: float = 1e-5, spatial_interpolation_scale: float = 1.875,
+                 temporal_interpolation_scale: float = 1.0, use_rotary_positional_embeddings: bool = False,
+                 use_learned_positional_embeddings: bool = False, id_pool_resample_learnable: Optional[bool] = False,
+                 device=None, dtype=None):
+        super().__init__()
+        if activation_fn != "gelu-approximate" or timestep_activation_fn != "silu" or not attention_bias \
+                or not norm_elementwise_affine or dropout != 0.0:
+            raise ValueError("unsupported configuration: the B200 path implements the CogVideoX-5B-I2V block exactly")
+        fk = dict(device=device, dtype=dtype)
+        self._build(False, num_attention_heads, attention_head_dim, in_channels, out_channels, flip_sin_to_cos, freq_shift,
+                    time_embed_dim, text_embed_dim, num_layers, sample_width, sample_height, sample_frames, patch_size,
+                    temporal_compression_ratio, max_text_seq_length, norm_eps, use_rotary_positional_embeddings,
+                    use_learned_positional_embeddings, bool(id_pool_resample_learnable), fk)
+
+    forward = transformer_forward
+
+
+class CogvideoXBranchModel(_Base):
+    """Same constructor arguments as the reference class (BR:46-77)."""
+
+    def __init__(self, num_attention_heads: int = 30, attention_head_dim: int = 64, in_channels: int = 16,
+                 out_channels: Optional[int] = 16, flip_sin_to_cos: bool = True, freq_shift: int = 0,
+                 time_embed_dim: int = 512, text_embed_dim: int = 4096, num_layers: int = 30, dropout: float = 0.0,
+                 attention_bias: bool = True, sample_width: int = 90, sample_height: int = 60, sample_frames: int = 49,
+                 patch_size: int = 2, temporal_compression_ratio: int = 4, max_text_seq_length: int = 226,
+                 activation_fn: str = "gelu-approximate", timestep_activation_fn: str = "silu",
+                 norm_elementwise_affine: bool = True, norm_eps: float = 1e-5, spatial_interpolation_scale: float = 1.875,
+                 temporal_interpolation_scale: float = 1.0, use_rotary_positional_embeddings: bool = False,
+                 use_learned_positional_embeddings: bool = False, wo_text: bool = False,
+                 id_pool_resample_learnable: bool = False, device=None, dtype=None):
+        super().__init__()
+        if wo_text:
+            raise ValueError("wo_text branches are not supported")
+        fk = dict(device=device, dtype=dtype)
+        self._build(True, num_attention_heads, attention_head_dim, in_channels, out_channels, flip_sin_to_cos, freq_shift,
+                    time_embed_dim, text_embed_dim, num_layers, sample_width, sample_height, sample_frames, patch_size,
+                    temporal_compression_ratio, max_text_seq_length, norm_eps, use_rotary_positional_embeddings,
+                    use_learned_positional_embeddings, False, fk)
+
+    forward = branch_forward
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# patching the reference's own classes
+# ------------------------------------------------------------------------------------------------------------------
+def install() -> None:
+    """Patch `forward` of the diffusers-fork classes in place (class level), so every pipeline / script of the reference
+    that calls `self.branch(...)` / `self.transformer(...)` (PIPE:947-980) runs on the B200 kernels unchanged."""
+    from diffusers.models.branch_cogvideox import CogvideoXBranchModel as RefBranch          # type: ignore
+    from diffusers.models.transformers.cogvideox_transformer_3d import CogVideoXTransformer3DModel as RefT3D  # type: ignore
+    try:
+        from diffusers.models.branch_cogvideox import CogvideoxBranchOutput as RB              # type: ignore
+        from diffusers.models.modeling_outputs import Transformer2DModelOutput as RT           # type: ignore
+        _REF_OUTPUTS["CogvideoxBranchOutput"] = RB
+        _REF_OUTPUTS["Transformer2DModelOutput"] = RT
+    except Exception:   # pragma: no cover - output classes are optional
+        pass
+    if not hasattr(RefT3D, "_vp_reference_forward"):
+        RefT3D._vp_reference_forward = RefT3D.forward
+        RefBranch._vp_reference_forward = RefBranch.forward
+    RefT3D.forward = transformer_forward
+    RefBranch.forward = branch_forward
+
+
+def uninstall() -> None:
+    from diffusers.models.branch_cogvideox import CogvideoXBranchModel as RefBranch          # type: ignore
+    from diffusers.models.transformers.cogvideox_transformer_3d import CogVideoXTransformer3DModel as RefT3D  # type: ignore
+    if hasattr(RefT3D, "_vp_reference_forward"):
+        RefT3D.forward = RefT3D._vp_reference_forward
+        RefBranch.forward = RefBranch._vp_reference_forward
