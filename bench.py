@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""Benchmark of the denoising hot path (BASELINE.json metric: denoise steps/s at 49x480x720 with CFG).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's B200 path
+    python bench.py --impl reference [--steps K] [--warmup W]      # reference algorithm on the host CPU (oracle port)
+
+One "step" = one `branch(...)` + one `transformer(...)` call at CFG batch 2 on the CogVideoX-5B-I2V shape with the 2-layer
+VideoPainter branch (PIPE:947-980), random-init bf16 weights, synthetic inputs.  Prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FULL = dict(num_attention_heads=48, attention_head_dim=64, in_channels=32, out_channels=16, time_embed_dim=512,
+            text_embed_dim=4096, num_layers=42, sample_width=90, sample_height=60, sample_frames=49, patch_size=2,
+            max_text_seq_length=226, use_rotary_positional_embeddings=True, use_learned_positional_embeddings=True)
+BRANCH_LAYERS = 2
+S_TEXT, S_VIDEO, D_MODEL = 226, 13 * 30 * 45, 3072
+S_TOTAL = S_TEXT + S_VIDEO
+
+
+def step_flops(batch: int, layers: int = 42 + BRANCH_LAYERS) -> float:
+    """Algorithmic FLOPs of one step: per block per sample 24 S D^2 + 4 S^2 D, plus embeds / heads."""
+    S, D = S_TOTAL, D_MODEL
+    block = 24.0 * S * D * D + 4.0 * S * S * D
+    extra = 2.0 * S_VIDEO * 128 * D + 2.0 * S_VIDEO * 132 * D + 2 * 2.0 * S_TEXT * 4096 * D \
+        + BRANCH_LAYERS * 2.0 * S_VIDEO * D * D + 2.0 * S_VIDEO * D * 64
+    return batch * (layers * block + extra)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle port on the host cores
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_block_seconds(repeats: int, seq_video_frames: int = 13) -> float:
+    """Median time of ONE full-size CogVideoXBlock forward (D=3072, 48x64 heads, S=17 776, batch 1, fp32) with the
+    oracle restatement on all host threads."""
+    import torch
+    from oracle import cogvideox_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    cfg = O.full_config(num_layers=1)
+    g = torch.Generator().manual_seed(0)
+    sd = {k: v for k, v in O.init_state_dict(cfg, 7).items() if k.startswith("transformer_blocks.0.")}
+    h = torch.randn(1, S_VIDEO, D_MODEL, generator=g)
+    e = torch.randn(1, S_TEXT, D_MODEL, generator=g)
+    temb = torch.randn(1, 512, generator=g)
+    rope = O.pipeline_rope(cfg, 480, 720, 13)
+    times = []
+    with torch.no_grad():
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            O.block(sd, "transformer_blocks.0.", cfg, h, e, temb, rope, head_chunk=4)
+            times.append(time.perf_counter() - t0)
+    times.sort()
+    return times[len(times) // 2]
+
+
+def cpu_baseline_record(block_s: float) -> dict:
+    blocks_per_step = (42 + BRANCH_LAYERS) * 2
+    return {"value": 1.0 / (block_s * blocks_per_step), "unit": "steps/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"one full-size CogVideoXBlock forward (fp32, batch 1, S=17776) = {block_s:.2f} s on the host; "
+                      f"steps/s = 1 / ({blocks_per_step} block-samples x that), embeds/head ignored"}
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    times = []
+    for i in range(args.warmup + args.steps):
+        t = cpu_block_seconds(1)
+        if i >= args.warmup:
+            times.append(t)
+    block_s = sum(times) / len(times)
+    rec = cpu_baseline_record(block_s)
+    out = {"impl": "reference", "metric": "denoise steps/s (49x480x720, CFG)", "value": rec["value"], "unit": "steps/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / rec["value"],
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+           "config": {"workload": "CogVideoX-5B-I2V + 2-layer VideoPainter branch, 49x480x720, CFG batch 2; each timed step is "
+                                  "a bounded sample: one full-size block (see cpu_baseline.sample)"},
+           "cpu_baseline": rec,
+           "e2e": {"value": rec["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------------------------
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--layers", type=int, default=42, help="(debug only) fewer layers -> line is marked invalid")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--breakdown", default=None, help="write the per-kernel breakdown JSON to this path")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import videopainter_b200 as vp
+    from videopainter_b200 import ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from videopainter_b200 import parallel
+    plan = parallel.make_plan(world, rank)
+
+    bf16 = torch.bfloat16
+    torch.manual_seed(1234)
+    cfg = dict(FULL, num_layers=args.layers)
+    tr = vp.CogVideoXTransformer3DModel(**cfg, device=dev, dtype=bf16)
+    br = vp.CogvideoXBranchModel(**dict(FULL, num_layers=BRANCH_LAYERS), device=dev, dtype=bf16)
+    with torch.no_grad():
+        for m in (tr, br):
+            m.patch_embed.pos_embedding.normal_(0, 0.5)
+    B_global = 2
+    B = plan.local_batch(B_global)
+
+    # synthetic inputs of the pipeline's shapes (PIPE:937-945), pinned on the host for the end-to-end leg
+    g = torch.Generator().manual_seed(99)
+    host = {
+        "latents": torch.randn(B, 13, 16, 60, 90, generator=g).to(bf16),
+        "image": torch.randn(B, 13, 16, 60, 90, generator=g).to(bf16),
+        "masked": torch.randn(B, 13, 16, 60, 90, generator=g).to(bf16),
+        "mask": (torch.rand(B, 13, 1, 60, 90, generator=g) > 0.75).to(bf16),
+        "text": torch.randn(B, 226, 4096, generator=g).to(bf16),
+        "timestep": torch.full((B,), 999, dtype=torch.int64),
+    }
+    host = {k: v.pin_memory() for k, v in host.items()}
+    from videopainter_b200.rope import pipeline_rope
+    rope = tuple(t.to(dev) for t in pipeline_rope(64, 480, 720, 13))
+    out_host = torch.empty(B, 13, 16, 60, 90, dtype=torch.float32).pin_memory()
+
+    def step(d):
+        lat_in = torch.cat([d["latents"], d["image"]], dim=2)
+        cond = torch.cat([d["masked"], d["mask"]], dim=2)
+        samples = br(hidden_states=d["latents"], encoder_hidden_states=d["text"], branch_cond=cond, timestep=d["timestep"],
+                     image_rotary_emb=rope, return_dict=False)[0]
+        noise, hs, rmask = tr(hidden_states=lat_in, encoder_hidden_states=d["text"], timestep=d["timestep"],
+                              image_rotary_emb=rope, branch_block_samples=samples, branch_block_masks=d["mask"],
+                              return_hidden_states=True, return_resample_mask=True, return_dict=False)
+        return noise
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    resident = {k: v.to(dev) for k, v in host.items()}
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            step(resident)
+        # ---------------- device-resident timing (value) ----------------
+        barrier()
+        sampler = ClockSampler(local)
+        sampler.start()
+        launches0 = ops.launch_count
+        ops.start_profile()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step(resident)
+        e1.record()
+        barrier()
+        clocks = sampler.stop()
+        prof = ops.stop_profile()
+        launches = ops.launch_count - launches0
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms_per_step = ms.item() / args.steps
+
+        # ---------------- end-to-end timing: host buffers in, host result out ----------------
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+            noise = step(d)
+            out_host.copy_(noise.float(), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        e1.record()
+        barrier()
+        ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+        e2e_ms = ms2.item() / args.steps
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    d2h = out_host.numel() * out_host.element_size()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback 1.4 PFLOP/s"
+    breakdown = {}
+    tot_ms = sum(v[1] for v in prof.values())
+    for name, (n, t, w) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+        breakdown[name] = {"launches": n, "ms_per_step": t / args.steps, "share": t / tot_ms if tot_ms else 0.0,
+                           "avg_launch_ms": t / n, "tflops": (w / (t * 1e-3) / 1e12) if (w and name != "ln_modulate") else None,
+                           "gbs": (w / (t * 1e-3) / 1e9) if name == "ln_modulate" else None}
+    dom = max(prof.items(), key=lambda kv: kv[1][1])
+    dn, (n_l, t_l, w_l) = dom
+    achieved = w_l / (t_l * 1e-3) / 1e12
+    roofline = {"kernel": dn, "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
+                "flops_per_launch": w_l / n_l, "avg_launch_ms": t_l / n_l, "share_of_step": t_l / tot_ms}
+    flops = step_flops(B_global, args.layers + BRANCH_LAYERS)
+    out = {"metric": "denoise steps/s (49x480x720, CFG)", "value": 1000.0 / ms_per_step, "unit": "steps/s", "n_gpus": world,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+           "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+           "config": {"workload": "CogVideoX-5B-I2V (42 layers, 48x64 heads) + 2-layer VideoPainter branch, one denoise step at "
+                                  "49x480x720 (17776 tokens), CFG batch 2, return_hidden_states=True as PIPE:967-980",
+                      "parallelism": plan.describe(), "l2": "per-step working set (11.7 GB weights, 218 MB activations per "
+                      "layer) exceeds the 126 MB L2; no explicit flush", "random_init": True},
+           "step_tflops": flops / (ms_per_step * 1e-3) / 1e12,
+           "frac_of_bf16_peak": {"sustained": flops / (ms_per_step * 1e-3) / 1e12 / peak_tf,
+                                 "burst": flops / (ms_per_step * 1e-3) / 1e12 / peaks.get("bf16_tflops", 1650.0)},
+           "roofline": roofline, "clocks": clocks, "gpu_launches": launches,
+           "e2e": {"value": 1000.0 / e2e_ms, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                   "ms_per_step": e2e_ms}}
+    if args.layers != 42:
+        out["invalid"] = "debug run with fewer layers than the named config"
+    if not args.no_cpu_baseline and world == 1:
+        out["cpu_baseline"] = cpu_baseline_record(cpu_block_seconds(1))
+    if args.breakdown:
+        with open(args.breakdown, "w") as f:
+            json.dump({"ms_per_step": ms_per_step, "kernels": breakdown, "clocks": clocks}, f, indent=1)
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -11,6 +11,49 @@ from ._lib import check, lib
 
 BF16 = torch.bfloat16
 
+# ---- optional per-op device timing (bench.py): CUDA events on the launching stream around every C-ABI call ----------
+_prof = None          # None, or dict name -> list[(start_event, end_event, work)]
+launch_count = 0      # kernels launched through this module since import (bench.py reports the delta)
+
+
+def start_profile() -> None:
+    global _prof
+    _prof = {}
+
+
+def stop_profile():
+    """Returns {name: (launches, total_ms, total_work)}; call after a device synchronise."""
+    global _prof
+    out = {}
+    for name, recs in (_prof or {}).items():
+        out[name] = (len(recs), sum(a.elapsed_time(b) for a, b, _ in recs), sum(w for _, _, w in recs))
+    _prof = None
+    return out
+
+
+def _timed(name, work_fn=None):
+    def deco(fn):
+        def wrapper(*args, **kwargs):
+            global launch_count
+            launch_count += 1
+            if _prof is None:
+                return fn(*args, **kwargs)
+            a = torch.cuda.Event(enable_timing=True)
+            b = torch.cuda.Event(enable_timing=True)
+            a.record()
+            r = fn(*args, **kwargs)
+            b.record()
+            _prof.setdefault(name, []).append((a, b, work_fn(*args, **kwargs) if work_fn else 0.0))
+            return r
+        wrapper.__name__ = fn.__name__
+        wrapper.__doc__ = fn.__doc__
+        return wrapper
+    return deco
+
+
+def _gemm_flops(a, w, bias, out, m, n, k, *args, **kwargs):
+    return 2.0 * m * n * k
+
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
@@ -28,6 +71,7 @@ def _p(t: Optional[torch.Tensor], dtype=None, name: str = "tensor") -> Optional[
     return t.data_ptr()
 
 
+@_timed('time_sinusoid')
 def time_sinusoid(timestep: torch.Tensor, dim: int, flip_sin_to_cos: bool, freq_shift: float) -> torch.Tensor:
     B = timestep.shape[0]
     out = torch.empty(B, dim, dtype=torch.float32, device=timestep.device)
@@ -40,6 +84,7 @@ def time_sinusoid(timestep: torch.Tensor, dim: int, flip_sin_to_cos: bool, freq_
     return out
 
 
+@_timed('gemv')
 def gemv(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], act_silu: bool,
          out: Optional[torch.Tensor] = None) -> torch.Tensor:
     B, K = x.shape
@@ -51,6 +96,7 @@ def gemv(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], ac
     return out
 
 
+@_timed('ln_modulate', lambda x, xbr, xro, y, batch, rpb, dim, *a, **k: 4.0 * batch * rpb * dim)
 def ln_modulate(x: torch.Tensor, x_batch_rows: int, x_row_offset: int, y: torch.Tensor, batch: int, rows_per_batch: int,
                 dim: int, gamma, beta, eps: float, mod: Optional[torch.Tensor], offs=(0, 0, 0, 0), text_len: int = 0):
     """offs = (shift_video, scale_video, shift_text, scale_text) element offsets into one batch row of `mod`."""
@@ -61,6 +107,7 @@ def ln_modulate(x: torch.Tensor, x_batch_rows: int, x_row_offset: int, y: torch.
     return y
 
 
+@_timed('ln_final')
 def ln_final(x, x_batch_rows, x_row_offset, y, batch, rows_per_batch, dim, g1, b1, g2, b2, eps, mod, shift_off, scale_off):
     check(lib().vp_ln_final(_p(x, BF16, "lnf.x"), x_batch_rows, x_row_offset, _p(y, BF16, "lnf.y"), batch, rows_per_batch, dim,
                             _p(g1, BF16), _p(b1, BF16), _p(g2, BF16), _p(b2, BF16), float(eps),
@@ -68,6 +115,7 @@ def ln_final(x, x_batch_rows, x_row_offset, y, batch, rows_per_batch, dim, g1, b
     return y
 
 
+@_timed('gemm_bias', _gemm_flops)
 def gemm_bias(a, w, bias, out, m, n, k, rows_per_batch, out_batch_rows, out_row_offset, alpha=1.0, lda=None, ldw=None, ldo=None):
     check(lib().vp_gemm_bias(_p(a, BF16, "gemm.a"), lda or k, _p(w, BF16, "gemm.w"), ldw or k, _p(bias, BF16, "gemm.bias"),
                              _p(out, BF16, "gemm.out"), ldo or n, m, n, k, rows_per_batch, out_batch_rows, out_row_offset,
@@ -75,12 +123,14 @@ def gemm_bias(a, w, bias, out, m, n, k, rows_per_batch, out_batch_rows, out_row_
     return out
 
 
+@_timed('gemm_gelu', _gemm_flops)
 def gemm_gelu(a, w, bias, out, m, n, k):
     check(lib().vp_gemm_gelu(_p(a, BF16, "gemm.a"), k, _p(w, BF16, "gemm.w"), k, _p(bias, BF16, "gemm.bias"),
                              _p(out, BF16, "gemm.out"), n, m, n, k, _stream()), "vp_gemm_gelu")
     return out
 
 
+@_timed('gemm_gate_residual', _gemm_flops)
 def gemm_gate_residual(a, w, bias, out, m, n, k, rows_per_batch, out_batch_rows, out_row_offset, res, res_batch_rows,
                        res_row_offset, gate=None, gate_video_off=0, gate_text_off=0, text_len=0, inject=None,
                        inject_batch_stride=0, ldi=0, inject_mask=None, video_len=0, lda=None, ldw=None):
@@ -93,6 +143,7 @@ def gemm_gate_residual(a, w, bias, out, m, n, k, rows_per_batch, out_batch_rows,
     return out
 
 
+@_timed('gemm_qkv', lambda a, w, bias, m, k, batch_rows, heads, qkv_first, *r, **kw: 2.0 * m * k * (3 - qkv_first) * heads * 64)
 def gemm_qkv(a, w, bias, m, k, batch_rows, heads, qkv_first, q_out, k_out, v_out, norm_q, norm_k, qk_eps, rope, text_len,
              k2_out=None, v2_out=None, mask2=None, row_scale=None, ldw=None):
     cos, sin = (None, None) if rope is None else rope
@@ -104,6 +155,7 @@ def gemm_qkv(a, w, bias, m, k, batch_rows, heads, qkv_first, q_out, k_out, v_out
         float(qk_eps), _p(cos, torch.float32, "rope.cos"), _p(sin, torch.float32, "rope.sin"), text_len, _stream()), "vp_gemm_qkv")
 
 
+@_timed('attention', lambda q, k0, v0, out, batch, heads, seq_q, kv_len0, scale, k1=None, v1=None, kv_len1=0, **kw: 4.0 * batch * heads * seq_q * (kv_len0 + kv_len1) * 64)
 def attention(q, k0, v0, out, batch, heads, seq_q, kv_len0, softmax_scale, k1=None, v1=None, kv_len1=0, out_scale=1.0,
               accumulate=False, ldo=None):
     check(lib().vp_attention(_p(q, BF16, "attn.q"), _p(k0, BF16, "attn.k"), _p(v0, BF16, "attn.v"), kv_len0, _p(k1, BF16), _p(v1, BF16),
@@ -112,6 +164,7 @@ def attention(q, k0, v0, out, batch, heads, seq_q, kv_len0, softmax_scale, k1=No
     return out
 
 
+@_timed('patchify')
 def patchify(src0, src1, out, bf, h, w, kpad):
     c0 = src0.shape[-3]
     c1 = 0 if src1 is None else src1.shape[-3]
@@ -120,11 +173,13 @@ def patchify(src0, src1, out, bf, h, w, kpad):
     return out
 
 
+@_timed('mask_pool')
 def mask_pool(mask, out, bf, h, w):
     check(lib().vp_mask_pool(_p(mask, BF16, "mask"), bf, h, w, _p(out, torch.uint8), _stream()), "vp_mask_pool")
     return out
 
 
+@_timed('unpatchify')
 def unpatchify(proj, out, bf, c, h, w):
     check(lib().vp_unpatchify(_p(proj, BF16, "unpatchify.proj"), bf, c, h, w, _p(out, BF16), _stream()), "vp_unpatchify")
     return out
