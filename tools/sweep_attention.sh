@@ -1,0 +1,5 @@
+# development aid: time differently-tuned builds of the attention kernel (csrc/libvp_b200_<name>.so)
+for v in "$@"; do
+  echo "== $v"
+  VP_B200_LIB=$PWD/videopainter_b200/csrc/libvp_b200_$v.so timeout 120 python tests/prof_kernels.py --only attention_S --iters 5 2>&1 | tail -1
+done

@@ -5,7 +5,10 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-from .build import LIB
+from .build import LIB as _DEFAULT_LIB
+
+# VP_B200_LIB selects a differently-tuned build of the SAME kernels (development aid); there is still no fallback.
+LIB = os.environ.get("VP_B200_LIB", _DEFAULT_LIB)
 
 _c_void_p, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 

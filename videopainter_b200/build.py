@@ -21,6 +21,18 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_variant(name: str, defines) -> str:
+    """Development aid: a differently-tuned copy of the library (csrc/libvp_b200_<name>.so), selected at run time with
+    the VP_B200_LIB environment variable (see _lib.py)."""
+    out = os.path.join(CSRC, f"libvp_b200_{name}.so")
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    cmd = [nvcc] + NVCC_FLAGS + [f"-D{d}" for d in defines] + SOURCES + ["-o", out]
+    r = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB

@@ -40,31 +40,34 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+// The *_a variants take a shared-window address computed once (smem_u32): inside hot loops the generic-pointer forms
+// make the compiler re-derive the window base every iteration.
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) { mbar_arrive_a(smem_u32(bar)); }
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(bar), "r"(parity)
       : "memory");
   return ok != 0;
 }
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) { return mbar_try_wait_a(smem_u32(bar), parity); }
 __device__ __forceinline__ uint64_t global_timer_ns() {
   uint64_t t;
   asm volatile("mov.u64 %0, %globaltimer;\n" : "=l"(t));
   return t;
 }
 // Bounded wait: a pipeline-protocol bug traps (kernel fails with an error) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+__device__ __forceinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   uint64_t t0 = 0;
   uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
+  while (!mbar_try_wait_a(bar, parity)) {
     if ((++spins & 0x3fff) == 0) {
       uint64_t now = global_timer_ns();
       if (t0 == 0) t0 = now;
@@ -72,6 +75,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
   }
 }
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait_a(bar, parity)) return;
+  if (mbar_try_wait_a(bar, parity)) return;
+  mbar_wait_slow(bar, parity);
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { mbar_wait_a(smem_u32(bar), parity); }
 
 // ------------------------------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor), loads only; results are written with plain vector stores
@@ -194,6 +203,11 @@ __device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t* v) {
       "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31};\n" ::VP_W4(v, 0),
       VP_W4(v, 4), VP_W4(v, 8), VP_W4(v, 12), VP_W4(v, 16), VP_W4(v, 20), VP_W4(v, 24), VP_W4(v, 28), "r"(taddr)
       : "memory");
+}
+__device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%8], {%0, %1, %2, %3, %4, %5, %6, %7};\n" ::VP_W4(v, 0), VP_W4(v, 4),
+               "r"(taddr)
+               : "memory");
 }
 __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t* v) {
   asm volatile(

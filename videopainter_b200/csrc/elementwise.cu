@@ -32,7 +32,7 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 //   y = LN(x; gamma, beta, eps) * (1 + scale[b, e]) + shift[b, e]        e = text if s < text_len else video
 // ------------------------------------------------------------------------------------------------------------------
 template <int CH>
-__global__ void __launch_bounds__(256) ln_modulate_kernel(const LnModParams p) {
+__global__ void __launch_bounds__(256, (CH <= 8 ? 3 : (CH <= 12 ? 2 : 1))) ln_modulate_kernel(const LnModParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + warp;
   if (row >= p.rows) return;
@@ -42,26 +42,32 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const LnModParams p) {
   __nv_bfloat16* y = p.y + row * p.D;
   const int nchunk = p.D >> 3;   // 8-element chunks in the row
 
-  float v[CH][8];
+  // the row stays packed (bf16) in registers: 4 registers per chunk keep the occupancy high enough to cover HBM latency
+  uint4 raw[CH];
   float sum = 0.f;
 #pragma unroll
   for (int i = 0; i < CH; ++i) {
     const int c = lane + i * 32;
-    if (c < nchunk) {
-      unpack8(ldg_nc_v4(x + c * 8), v[i]);
+    raw[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (c < nchunk) raw[i] = ldg_nc_v4(x + c * 8);
+  }
 #pragma unroll
-      for (int e = 0; e < 8; ++e) sum += v[i][e];
-    }
+  for (int i = 0; i < CH; ++i) {
+    float v[8];
+    unpack8(raw[i], v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) sum += v[e];                 // padding chunks are zero
   }
   const float mean = warp_sum(sum) / (float)p.D;
   float sq = 0.f;
 #pragma unroll
   for (int i = 0; i < CH; ++i) {
-    const int c = lane + i * 32;
-    if (c < nchunk) {
+    if (lane + i * 32 < nchunk) {
+      float v[8];
+      unpack8(raw[i], v);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        const float d = v[i][e] - mean;
+        const float d = v[e] - mean;
         sq += d * d;
       }
     }
@@ -75,11 +81,12 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const LnModParams p) {
   for (int i = 0; i < CH; ++i) {
     const int c = lane + i * 32;
     if (c < nchunk) {
-      float g[8], be[8], o[8];
+      float v[8], g[8], be[8], o[8];
+      unpack8(raw[i], v);
       unpack8(__ldg(reinterpret_cast<const uint4*>(p.gamma) + c), g);
       unpack8(__ldg(reinterpret_cast<const uint4*>(p.beta) + c), be);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) o[e] = (v[i][e] - mean) * rstd * g[e] + be[e];
+      for (int e = 0; e < 8; ++e) o[e] = (v[e] - mean) * rstd * g[e] + be[e];
       if (shift) {
         const float4 s0 = __ldg(reinterpret_cast<const float4*>(shift + c * 8));
         const float4 s1 = __ldg(reinterpret_cast<const float4*>(shift + c * 8) + 1);

@@ -218,41 +218,45 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // The producer and MMA loops run warp-wide (uniform control flow) and only the asynchronous instructions themselves
+  // are issued by one elected lane: descriptor / coordinate arithmetic then stays on the uniform datapath, which is what
+  // keeps the tcgen05.mma issue rate at the tensor pipe's own rate (a single divergent thread costs ~100 clk per MMA).
   if (warp == 0) {
     // ------------------------------------------------ TMA producer ------------------------------------------------
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        int m_blk, n_blk;
-        tile_coords(tile, m_tiles, n_tiles, p.group_m, m_blk, n_blk);
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int m_blk, n_blk;
+      tile_coords(tile, m_tiles, n_tiles, p.group_m, m_blk, n_blk);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (elect_one()) {
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
           mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
           tma_load_2d(sa, &tmap_a, &full[stage], kb * BK, m_blk * BM, kEvictNormal);
           tma_load_2d(sb, &tmap_b, &full[stage], kb * BK, n_blk * BN, kEvictLast);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------ MMA issuer --------------------------------------------------
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(&tempty[acc], acc_phase ^ 1);
+    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
+        if (elect_one()) {
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint64_t adesc = make_desc_sw128(sa, 1024, 0);
           const uint64_t bdesc = make_desc_sw128(sa + A_BYTES, 1024, 0);
@@ -262,10 +266,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             mma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           }
           tc_commit(&empty[stage]);   // frees the smem stage once these MMAs have read it
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        tc_commit(&tfull[acc]);       // accumulator complete -> epilogue
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      if (elect_one()) tc_commit(&tfull[acc]);       // accumulator complete -> epilogue
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // ------------------------------------------------ epilogue ----------------------------------------------------
