@@ -171,7 +171,7 @@ def main() -> None:
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     from videopainter_b200 import parallel
-    plan = parallel.make_plan(world, rank)
+    plan = parallel.init(world, rank).plan        # CFG halves on disjoint GPU groups x Ulysses inside each (parallel.py)
 
     bf16 = torch.bfloat16
     torch.manual_seed(1234)
@@ -182,7 +182,7 @@ def main() -> None:
         for m in (tr, br):
             m.patch_embed.pos_embedding.normal_(0, 0.5)
     B_global = 2
-    B = plan.local_batch(B_global)
+    B = B_global          # every rank is handed the whole CFG batch, as the pipeline would; the model takes its share
 
     # synthetic inputs of the pipeline's shapes (PIPE:937-945), pinned on the host for the end-to-end leg
     g = torch.Generator().manual_seed(99)

@@ -74,24 +74,37 @@ int vp_gemm_gelu(const void* a, long long lda, const void* w, long long ldw, con
 /* out = res + gate[b, expert(s)] * (A W^T + bias) [+ inject[b, s - text_len] where inject_mask == 0]
  * — attention out-proj + gated residual (AP:2202, T3D:169-170), FFN-2 + gated residual + branch injection
  * (ATT:1201, T3D:181-182, 596-609), and patch-embed conv + positional table (EMB:410-451; gate = null).
- * gate is fp32: gate[b * gate_batch_stride + (s < text_len ? gate_text_off : gate_video_off) + n]. */
+ * gate is fp32: gate[b * gate_batch_stride + (s < text_len ? gate_text_off : gate_video_off) + n].
+ * a_k_chunk / a_chunk_stride: A may arrive split along K in chunks of a_k_chunk columns that lie a_chunk_stride
+ * elements apart (the Ulysses all-to-all delivers the attention output as [peer][row][heads_per_peer * 64]);
+ * a_k_chunk = 0 (or k) means a plain [m, k] matrix. */
 int vp_gemm_gate_residual(const void* a, long long lda, const void* w, long long ldw, const void* bias, void* out, int ldo,
                           int m, int n, int k, int rows_per_batch, long long out_batch_rows, int out_row_offset,
                           const void* res, int ldr, long long res_batch_rows, int res_row_offset, const float* gate,
                           long long gate_batch_stride, int gate_video_off, int gate_text_off, int text_len,
                           const void* inject, long long inject_batch_stride, int ldi, const uint8_t* inject_mask,
-                          int video_len, void* stream);
+                          int video_len, int a_k_chunk, long long a_chunk_stride, void* stream);
 
 /* Fused to_q/to_k/to_v + QK LayerNorm(64) + 3D RoPE (AP:2132-2154), written head-major [B, H, S, 64].
  * w is [Wq; Wk; Wv] (qkv_first = 0) or [Wk; Wv] (qkv_first = 1, previous-window keys AP:2157-2172, 2247-2252).
  * row_scale[m] (nullable) multiplies the projection before the norm (prev_resample_mask * prev_clip_weight).
  * k2_out/v2_out (nullable) receive the masked copy of the ID-resample processor: K2 = RoPE(norm_k(k * mask2)),
- * V2 = v * mask2 (AP:2255-2281). rope tables are fp32 [video_len, 64] (nullable). */
+ * V2 = v * mask2 (AP:2255-2281). rope tables are fp32 [video_len, 64] (nullable).
+ * heads_per_dest / dest_stride: head h of token s goes to
+ *   x_out + (h / heads_per_dest) * dest_stride + ((b * heads_per_dest + h % heads_per_dest) * batch_rows + s) * 64,
+ * i.e. heads_per_dest = heads (dest_stride ignored) is the plain [B, H, S, 64]; heads_per_dest = heads / P writes each
+ * Ulysses destination rank's heads into its own contiguous send block (no pack pass before the all-to-all). */
 int vp_gemm_qkv(const void* a, long long lda, const void* w, long long ldw, const void* bias, int m, int k, int batch_rows,
                 int heads, int qkv_first, void* q_out, void* k_out, void* v_out, void* k2_out, void* v2_out,
                 const uint8_t* mask2, const float* row_scale, const void* norm_q_w, const void* norm_q_b,
                 const void* norm_k_w, const void* norm_k_b, float qk_eps, const float* rope_cos, const float* rope_sin,
-                int text_len, void* stream);
+                int text_len, int heads_per_dest, long long dest_stride, void* stream);
+
+/* Ulysses receive side: src [peers][slots][heads_local][rows_per_peer][64] (what the all-to-all delivers when every peer
+ * sent its vp_gemm_qkv destination block) -> dst[slot] [heads_local][peers * rows_per_peer][64], the layout vp_attention
+ * reads.  slots <= 5 (q, k, v, k2, v2); dst pointers beyond `slots` are ignored. */
+int vp_a2a_unpack_heads(const void* src, void* dst0, void* dst1, void* dst2, void* dst3, void* dst4, int slots, int peers,
+                        int heads_local, int rows_per_peer, void* stream);
 
 /* softmax(Q K^T * scale) V over one or two K/V segments, d_head = 64, non-causal, unmasked (AP:2192-2197, 2285-2290).
  * q [B, H, seq_q, 64], k0/v0/k1/v1 [B, H, kv_len, 64]; out [B, seq_q, ldo] with head h at columns [64h, 64h + 64).

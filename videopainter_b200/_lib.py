@@ -24,10 +24,11 @@ SIGNATURES = {
     "vp_gemm_gelu": [_c_void_p, _ll, _c_void_p, _ll, _c_void_p, _c_void_p, _i, _i, _i, _i, _c_void_p],
     "vp_gemm_gate_residual": [_c_void_p, _ll, _c_void_p, _ll, _c_void_p, _c_void_p, _i, _i, _i, _i, _i, _ll, _i,
                               _c_void_p, _i, _ll, _i, _c_void_p, _ll, _i, _i, _i, _c_void_p, _ll, _i, _c_void_p, _i,
-                              _c_void_p],
+                              _i, _ll, _c_void_p],
     "vp_gemm_qkv": [_c_void_p, _ll, _c_void_p, _ll, _c_void_p, _i, _i, _i, _i, _i, _c_void_p, _c_void_p, _c_void_p,
                     _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _f,
-                    _c_void_p, _c_void_p, _i, _c_void_p],
+                    _c_void_p, _c_void_p, _i, _i, _ll, _c_void_p],
+    "vp_a2a_unpack_heads": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _i, _i, _i, _i, _c_void_p],
     "vp_attention": [_c_void_p, _c_void_p, _c_void_p, _i, _c_void_p, _c_void_p, _i, _c_void_p, _i, _i, _i, _i, _f, _f, _i,
                      _c_void_p],
     "vp_patchify": [_c_void_p, _i, _c_void_p, _i, _i, _i, _i, _c_void_p, _i, _c_void_p],

@@ -107,7 +107,7 @@ int vp_gemm_gate_residual(const void* a, long long lda, const void* w, long long
                           const void* res, int ldr, long long res_batch_rows, int res_row_offset, const float* gate,
                           long long gate_batch_stride, int gate_video_off, int gate_text_off, int text_len,
                           const void* inject, long long inject_batch_stride, int ldi, const uint8_t* inject_mask,
-                          int video_len, void* stream) {
+                          int video_len, int a_k_chunk, long long a_chunk_stride, void* stream) {
   VP_REQUIRE(a && w && out && res, VP_ERR_BAD_SHAPE, "gemm_gate_residual: null pointer");
   VP_REQUIRE(ldo % 8 == 0 && ldr % 8 == 0 && (inject == nullptr || ldi % 8 == 0), VP_ERR_BAD_ALIGN,
              "gemm_gate_residual: leading dims must be multiples of 8");
@@ -119,6 +119,7 @@ int vp_gemm_gate_residual(const void* a, long long lda, const void* w, long long
   p.text_len = text_len;
   p.inject = (const __nv_bfloat16*)inject; p.inject_batch_stride = inject_batch_stride; p.ldi = ldi;
   p.inject_mask = inject_mask; p.video_len = video_len;
+  p.a_k_chunk = a_k_chunk; p.a_chunk_stride = a_chunk_stride;
   return launch_gemm(EPI_RESID, a, lda, w, ldw, p, (cudaStream_t)stream);
 }
 
@@ -126,8 +127,10 @@ int vp_gemm_qkv(const void* a, long long lda, const void* w, long long ldw, cons
                 int heads, int qkv_first, void* q_out, void* k_out, void* v_out, void* k2_out, void* v2_out,
                 const uint8_t* mask2, const float* row_scale, const void* norm_q_w, const void* norm_q_b,
                 const void* norm_k_w, const void* norm_k_b, float qk_eps, const float* rope_cos, const float* rope_sin,
-                int text_len, void* stream) {
+                int text_len, int heads_per_dest, long long dest_stride, void* stream) {
   VP_REQUIRE(a && w && bias && k_out && v_out && norm_k_w && norm_k_b, VP_ERR_BAD_SHAPE, "gemm_qkv: null pointer");
+  VP_REQUIRE(heads_per_dest > 0 && heads % heads_per_dest == 0 && dest_stride % 8 == 0, VP_ERR_BAD_SHAPE,
+             "gemm_qkv: heads_per_dest must divide heads");
   VP_REQUIRE(qkv_first == 0 || qkv_first == 1, VP_ERR_BAD_SHAPE, "gemm_qkv: qkv_first must be 0 or 1");
   VP_REQUIRE(qkv_first == 1 || (q_out && norm_q_w && norm_q_b), VP_ERR_BAD_SHAPE, "gemm_qkv: q outputs missing");
   VP_REQUIRE((k2_out == nullptr) == (v2_out == nullptr) && (k2_out == nullptr || mask2 != nullptr), VP_ERR_BAD_SHAPE,
@@ -146,6 +149,7 @@ int vp_gemm_qkv(const void* a, long long lda, const void* w, long long ldw, cons
   p.qk_eps = qk_eps;
   p.rope_cos = rope_cos; p.rope_sin = rope_sin;
   p.text_len = text_len;
+  p.heads_per_dest = heads_per_dest; p.dest_stride = dest_stride;
   return launch_gemm(EPI_QKV, a, lda, w, ldw, p, (cudaStream_t)stream);
 }
 
@@ -160,6 +164,15 @@ int vp_attention(const void* q, const void* k0, const void* v0, int kv_len0, con
   p.out = (__nv_bfloat16*)out; p.ldo = ldo;
   p.out_scale = out_scale; p.accumulate = accumulate;
   return launch_attention(q, k0, v0, k1, v1, p, (cudaStream_t)stream);
+}
+
+int vp_a2a_unpack_heads(const void* src, void* dst0, void* dst1, void* dst2, void* dst3, void* dst4, int slots, int peers,
+                        int heads_local, int rows_per_peer, void* stream) {
+  VP_REQUIRE(src && dst0 && slots >= 1 && slots <= 5 && peers >= 1 && heads_local >= 1 && rows_per_peer >= 1, VP_ERR_BAD_SHAPE,
+             "a2a_unpack_heads: bad arguments");
+  void* dst[5] = {dst0, dst1, dst2, dst3, dst4};
+  for (int i = 0; i < slots; ++i) VP_REQUIRE(dst[i] != nullptr, VP_ERR_BAD_SHAPE, "a2a_unpack_heads: null destination");
+  return launch_a2a_unpack_heads(src, dst, slots, peers, heads_local, rows_per_peer, (cudaStream_t)stream);
 }
 
 int vp_patchify(const void* src0, int c0, const void* src1, int c1, int bf, int h, int w, void* out, int kpad, void* stream) {

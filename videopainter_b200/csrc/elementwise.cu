@@ -290,7 +290,37 @@ __global__ void unpatchify_kernel(const __nv_bfloat16* __restrict__ proj, int BF
   *reinterpret_cast<__nv_bfloat162*>(out + ((bf * C + c) * H + y) * (long long)W + 2 * px) = v;
 }
 
+// Ulysses receive side: [peer][slot][head][row][64] -> per slot [head][peer * rows + row][64]; one 16-byte vector per
+// thread, both sides read / written in whole 128-byte head rows.
+struct UnpackDst { __nv_bfloat16* p[5]; };
+__global__ void __launch_bounds__(256) a2a_unpack_heads_kernel(const uint4* __restrict__ src, UnpackDst dst, int slots, int peers,
+                                                               int heads, int rows) {
+  const long long total = (long long)peers * slots * heads * rows * 8;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(idx & 7);
+    long long r = idx >> 3;
+    const int row = (int)(r % rows); r /= rows;
+    const int h = (int)(r % heads); r /= heads;
+    const int slot = (int)(r % slots);
+    const int peer = (int)(r / slots);
+    uint4* d = reinterpret_cast<uint4*>(dst.p[slot]) + (((long long)h * peers + peer) * rows + row) * 8 + v;
+    *d = ldg_nc_v4(src + idx);
+  }
+}
+
 }  // namespace
+
+int launch_a2a_unpack_heads(const void* src, void* const* dst, int slots, int peers, int heads_local, int rows_per_peer,
+                            cudaStream_t st) {
+  UnpackDst d{};
+  for (int i = 0; i < slots; ++i) d.p[i] = (__nv_bfloat16*)dst[i];
+  const long long total = (long long)peers * slots * heads_local * rows_per_peer * 8;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  a2a_unpack_heads_kernel<<<(unsigned)blocks, 256, 0, st>>>((const uint4*)src, d, slots, peers, heads_local, rows_per_peer);
+  VP_CHECK_CUDA(cudaGetLastError());
+  return VP_OK;
+}
 
 int launch_ln_modulate(const LnModParams& p, cudaStream_t st) {
   VP_REQUIRE(p.rows > 0 && p.D > 0 && p.D % 8 == 0, VP_ERR_BAD_SHAPE, "ln_modulate: D must be a positive multiple of 8");

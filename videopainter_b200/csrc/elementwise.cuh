@@ -29,6 +29,8 @@ int launch_timestep_sinusoid(const long long* t_i64, const float* t_f32, float* 
                              cudaStream_t st);
 int launch_patchify(const void* src0, int C0, const void* src1, int C1, int BF, int H, int W, void* out, int Kpad, cudaStream_t st);
 int launch_mask_pool(const void* mask, int BF, int H, int W, uint8_t* out, cudaStream_t st);
+int launch_a2a_unpack_heads(const void* src, void* const* dst, int slots, int peers, int heads_local, int rows_per_peer,
+                            cudaStream_t st);
 int launch_unpatchify(const void* proj, int BF, int C, int H, int W, void* out, cudaStream_t st);
 
 }  // namespace vp

@@ -145,7 +145,8 @@ __device__ __forceinline__ void epilogue_qkv_head(const GemmParams& p, const uin
   const int which = n0 / p.d_model + p.qkv_first;      // 0 = Q, 1 = K, 2 = V
   const int head = (n0 % p.d_model) >> 6;
   const float rs = p.row_scale ? p.row_scale[m] : 1.0f;
-  const long long off = (((long long)b * p.heads + head) * p.rows_per_batch + s) * 64;
+  const int dest = head / p.heads_per_dest, hl = head - dest * p.heads_per_dest;
+  const long long off = dest * p.dest_stride + (((long long)b * p.heads_per_dest + hl) * p.rows_per_batch + s) * 64;
   if (which == 2) {
     float y[32];
 #pragma unroll
@@ -234,7 +235,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
           mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
-          tma_load_2d(sa, &tmap_a, &full[stage], kb * BK, m_blk * BM, kEvictNormal);
+          const int k0 = kb * BK, chunk = k0 / p.a_k_chunk;
+          tma_load_3d(sa, &tmap_a, &full[stage], k0 - chunk * p.a_k_chunk, m_blk * BM, chunk, kEvictNormal);
           tma_load_2d(sb, &tmap_b, &full[stage], kb * BK, n_blk * BN, kEvictLast);
         }
         __syncwarp();
@@ -352,12 +354,19 @@ int launch_gemm(int epi, const void* A, long long lda, const void* W, long long 
   VP_REQUIRE(p.N % 64 == 0, VP_ERR_BAD_SHAPE, "gemm: N must be a multiple of 64");
   VP_REQUIRE(p.K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, VP_ERR_BAD_ALIGN, "gemm: K / leading dims must be multiples of 8");
   VP_REQUIRE(p.rows_per_batch > 0, VP_ERR_BAD_SHAPE, "gemm: rows_per_batch");
+  GemmParams q = p;
+  if (q.a_k_chunk <= 0 || q.a_k_chunk >= q.K) {
+    q.a_k_chunk = q.K;
+    q.a_chunk_stride = (long long)q.K;       // unused: a single chunk
+  }
+  VP_REQUIRE(q.K % q.a_k_chunk == 0 && (q.a_k_chunk == q.K || q.a_k_chunk % BK == 0) && q.a_chunk_stride % 8 == 0, VP_ERR_BAD_SHAPE,
+             "gemm: K chunks of A must be multiples of 64 columns that divide K");
   CUtensorMap ta, tb;
   {
-    uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.M};
-    uint64_t str[1] = {(uint64_t)lda * 2};
-    uint32_t box[2] = {BK, BM};
-    int rc = make_tmap_bf16(&ta, A, 2, dims, str, box);
+    uint64_t dims[3] = {(uint64_t)q.a_k_chunk, (uint64_t)p.M, (uint64_t)(q.K / q.a_k_chunk)};
+    uint64_t str[2] = {(uint64_t)lda * 2, (uint64_t)q.a_chunk_stride * 2};
+    uint32_t box[3] = {BK, BM, 1};
+    int rc = make_tmap_bf16(&ta, A, 3, dims, str, box);
     if (rc) return rc;
   }
   {
@@ -367,8 +376,8 @@ int launch_gemm(int epi, const void* A, long long lda, const void* W, long long 
     int rc = make_tmap_bf16(&tb, W, 2, dims, str, box);
     if (rc) return rc;
   }
-  GemmParams q = p;
   if (q.group_m <= 0) q.group_m = 16;
+  if (q.heads_per_dest <= 0) q.heads_per_dest = q.heads > 0 ? q.heads : 1;
   switch (epi) {
     case EPI_BIAS: return launch_impl<EPI_BIAS>(ta, tb, q, st);
     case EPI_GELU: return launch_impl<EPI_GELU>(ta, tb, q, st);

@@ -15,6 +15,10 @@ enum GemmEpilogue : int {
 struct GemmParams {
   int M, N, K;
   int group_m;               // rasterisation: m-tiles per group (L2 reuse of A)
+  // A may be split along K into chunks of a_k_chunk columns that live a_chunk_stride elements apart (the attention output
+  // gathered from the Ulysses peers arrives as [peer][row][heads_per_peer * 64]); a_k_chunk = K means one plain matrix
+  int a_k_chunk;
+  long long a_chunk_stride;
   // logical row m -> batch b = m / rows_per_batch, token s = m % rows_per_batch
   int rows_per_batch;
   // ---- plain / gelu / residual output: row (b * out_batch_rows + out_row_offset + s), skipped if s + off < 0
@@ -42,6 +46,10 @@ struct GemmParams {
   int d_model;                    // H * 64
   int heads;
   int qkv_first;                  // 0: columns are [Q|K|V]; 1: columns are [K|V]
+  // head h is written to q_out + (h / heads_per_dest) * dest_stride + ((b * heads_per_dest + h % heads_per_dest) * S + s) * 64:
+  // heads_per_dest = heads gives the plain [B, H, S, 64]; smaller values lay the heads out per Ulysses destination rank
+  int heads_per_dest;
+  long long dest_stride;          // elements
   __nv_bfloat16* q_out;           // [B, H, S, 64]
   __nv_bfloat16* k_out;
   __nv_bfloat16* v_out;

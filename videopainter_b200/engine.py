@@ -16,7 +16,8 @@ from typing import Any, Dict, List, Optional, Sequence, Tuple
 
 import torch
 
-from . import ops
+from . import ops, parallel
+from .parallel import Shard, qkv_dest_stride, send_block_shape
 
 BF16 = torch.bfloat16
 
@@ -147,39 +148,59 @@ def pack_state_dict(sd: Dict[str, torch.Tensor], dims: Dims, device, lora_scale:
 # workspace
 # ------------------------------------------------------------------------------------------------------------------
 class _Workspace:
-    def __init__(self, pm: PackedModel, B: int, S: int, Sv: int, device):
+    """Scratch buffers of one (batch, shard) shape.  B = samples this rank runs, R = token rows it owns (R = S unless the
+    sequence is sharded), Hl = heads it attends (Hl = H unless sharded)."""
+
+    def __init__(self, pm: PackedModel, B: int, S: int, Sv: int, sh: Shard, device):
         D, H = pm.dims.D, pm.dims.heads
+        R, Hl, P = sh.rows, sh.heads_local, sh.sp
+        if P > 1 and B != 1:
+            raise ValueError("sequence parallelism runs one sample per rank (the CFG halves live on disjoint groups)")
         e = lambda *shape, dtype=BF16: torch.empty(*shape, dtype=dtype, device=device)   # noqa: E731
-        self.xn = e(B * S, D)
-        self.q = e(B, H, S, 64)
-        self.k = e(B, H, S, 64)
-        self.v = e(B, H, S, 64)
+        self.xn = e(B * R, D)
+        self.q = e(B, Hl, S, 64)
+        self.k = e(B, Hl, S, 64)
+        self.v = e(B, Hl, S, 64)
         self.k2 = None
         self.v2 = None
-        self.ao = e(B * S, D)
-        self.xmid = e(B, S, D)
-        self.ffm = e(B * S, 4 * D)
+        self.ao = e(B * S, Hl * 64)                     # attention output, token-major (send buffer of all-to-all #2)
+        self.xmid = e(B, R, D)
+        self.ffm = e(B * R, 4 * D)
         self.mod1 = e(B, 6 * D, dtype=torch.float32)
         self.mod2 = e(B, 6 * D, dtype=torch.float32)
         self.patches = e(B * Sv, pm.kpad)
         self.ping = [None, None]
         self.device = device
-        self.shape = (B, H, S)
+        self.shape = (B, Hl, S)
+        self.sh = sh
+        # Ulysses exchange buffers (allocated on first use)
+        self._send = {}
+        self._recv = {}
+        self.ao_recv = e(P, R, Hl * 64) if P > 1 else None
+        self.xfull = None
 
     def second_kv(self):
         if self.k2 is None:
-            B, H, S = self.shape
-            self.k2 = torch.empty(B, H, S, 64, dtype=BF16, device=self.device)
-            self.v2 = torch.empty(B, H, S, 64, dtype=BF16, device=self.device)
+            B, Hl, S = self.shape
+            self.k2 = torch.empty(B, Hl, S, 64, dtype=BF16, device=self.device)
+            self.v2 = torch.empty(B, Hl, S, 64, dtype=BF16, device=self.device)
         return self.k2, self.v2
 
+    def exchange(self, slots: int):
+        """(send, recv) buffers [P][slots][Hl][R][64] of the QKV all-to-all."""
+        if slots not in self._send:
+            shape = send_block_shape(self.sh, slots)
+            self._send[slots] = torch.empty(*shape, dtype=BF16, device=self.device)
+            self._recv[slots] = torch.empty(*shape, dtype=BF16, device=self.device)
+        return self._send[slots], self._recv[slots]
 
-def _workspace(pm: PackedModel, B, S, Sv, device) -> _Workspace:
-    key = (B, S, Sv, str(device))
+
+def _workspace(pm: PackedModel, B, S, Sv, sh: Shard, device) -> _Workspace:
+    key = (B, S, Sv, sh.sp, sh.sp_rank, str(device))
     ws = pm.workspace.get(key)
     if ws is None:
         pm.workspace.clear()
-        ws = _Workspace(pm, B, S, Sv, device)
+        ws = _Workspace(pm, B, S, Sv, sh, device)
         pm.workspace[key] = ws
     return ws
 
@@ -219,58 +240,113 @@ def _embed(pm: PackedModel, ws: _Workspace, x: torch.Tensor, text: torch.Tensor,
                            out_row_offset=0, res=pm.pos, res_batch_rows=0, res_row_offset=0)
 
 
-def _block(pm: PackedModel, blk: PackedBlock, ws: _Workspace, x_in: torch.Tensor, x_out: torch.Tensor, emb: torch.Tensor,
-           rope, B, S, St, Sv, resample_mask_u8=None, prev=None, prev_w=None, prev_mask=None, inject=None, inject_mask=None):
-    """CogVideoXBlock.forward T3D:125-184 (+ branch injection T3D:596-609 fused into the FFN-2 epilogue)."""
+def _embed_sharded(pm: PackedModel, ws: _Workspace, x_local: torch.Tensor, text, src0, src1, B, Fr, H, W, St, Sv):
+    """Patch / text embedding of the whole sequence (1.6 % of one block's FLOPs), of which this rank keeps its rows."""
+    sh = ws.sh
+    if sh.sp == 1:
+        _embed(pm, ws, x_local, text, src0, src1, B, Fr, H, W, St, Sv)
+        return
+    if ws.xfull is None:
+        ws.xfull = torch.empty(B, St + Sv, pm.dims.D, dtype=BF16, device=ws.device)
+    _embed(pm, ws, ws.xfull, text, src0, src1, B, Fr, H, W, St, Sv)
+    x_local.copy_(ws.xfull[:, sh.row0:sh.row0 + sh.rows])
+
+
+def _qkv(pm, blk, ws, xn, which_first, rope, mask2=None, row_scale=None, masked_copy=False, group=None):
+    """QKV projection + QK-norm + RoPE into the attention layout [B, Hl, S, 64]; under sequence parallelism through the
+    head-scatter all-to-all.  which_first = 0: q, k, v (+ masked k2, v2);  1: k, v of the previous window."""
     d = pm.dims
-    D, H = d.D, d.heads
-    M = B * S
+    sh = ws.sh
+    B, Hl, S = ws.shape
+    D, H, R = d.D, d.heads, sh.rows
+    M = B * R
+    w = blk.qkv_w if which_first == 0 else blk.qkv_w[D:]
+    b = blk.qkv_b if which_first == 0 else blk.qkv_b[D:]
+    nq = (blk.nq_w, blk.nq_b) if which_first == 0 else None
+    nk = (blk.nk_w, blk.nk_b)
+    rope_l, text_l = rope, sh.text_rows
+    if which_first == 0:
+        outs = [ws.q, ws.k, ws.v] + (list(ws.second_kv()) if masked_copy else [])
+    else:
+        outs = list(ws.second_kv())
+    if sh.sp == 1:
+        q_o = outs[0] if which_first == 0 else None
+        k_o, v_o = (outs[1], outs[2]) if which_first == 0 else (outs[0], outs[1])
+        k2_o, v2_o = (outs[3], outs[4]) if masked_copy else (None, None)
+        ops.gemm_qkv(xn, w, b, M, D, R, H, which_first, q_o, k_o, v_o, nq, nk, 1e-6, rope_l, text_l, k2_out=k2_o, v2_out=v2_o,
+                     mask2=mask2, row_scale=row_scale)
+        return
+    slots = len(outs)
+    send, recv = ws.exchange(slots)
+    sl = [send[0, i] for i in range(slots)]                      # destination 0's blocks; the kernel adds dest * dest_stride
+    q_o = sl[0] if which_first == 0 else None
+    k_o, v_o = (sl[1], sl[2]) if which_first == 0 else (sl[0], sl[1])
+    k2_o, v2_o = (sl[3], sl[4]) if masked_copy else (None, None)
+    ops.gemm_qkv(xn, w, b, M, D, R, H, which_first, q_o, k_o, v_o, nq, nk, 1e-6, rope_l, text_l, k2_out=k2_o, v2_out=v2_o,
+                 mask2=mask2, row_scale=row_scale, heads_per_dest=Hl, dest_stride=qkv_dest_stride(sh, slots))
+    group.all_to_all(recv, send)
+    ops.a2a_unpack_heads(recv, outs, sh.sp, Hl, R)
+
+
+def _block(pm: PackedModel, blk: PackedBlock, ws: _Workspace, x_in: torch.Tensor, x_out: torch.Tensor, emb: torch.Tensor,
+           rope, B, S, St, Sv, resample_mask_u8=None, prev=None, prev_w=None, prev_mask=None, inject=None, inject_mask=None,
+           group=None):
+    """CogVideoXBlock.forward T3D:125-184 (+ branch injection T3D:596-609 fused into the FFN-2 epilogue).  x_in / x_out are
+    this rank's rows [B, R, D]; St / Sv are the owned text / video row counts; S is the full sequence length."""
+    d = pm.dims
+    sh = ws.sh
+    D, Hl, R = d.D, sh.heads_local, sh.rows
+    M = B * R
     OFF1 = (0, D, 3 * D, 4 * D)       # shift, scale (video) / enc_shift, enc_scale (text) inside the 6D table
     ops.gemv(emb, blk.n1_lin_w, blk.n1_lin_b, act_silu=True, out=ws.mod1)
-    ops.ln_modulate(x_in, S, 0, ws.xn, B, S, D, blk.n1_w, blk.n1_b, d.eps, ws.mod1, OFF1, St)
+    ops.ln_modulate(x_in, R, 0, ws.xn, B, R, D, blk.n1_w, blk.n1_b, d.eps, ws.mod1, OFF1, St)
     use_prev = prev is not None and prev_w is not None and prev_w > 0.0
     scale = 1.0 / math.sqrt(d.head_dim)
+    ldo = Hl * 64
     if d.resample and not use_prev:                                   # AP:2255-2256: masked copy of own K/V
+        _qkv(pm, blk, ws, ws.xn, 0, rope, mask2=resample_mask_u8, masked_copy=True, group=group)
         k2, v2 = ws.second_kv()
-        ops.gemm_qkv(ws.xn, blk.qkv_w, blk.qkv_b, M, D, S, H, 0, ws.q, ws.k, ws.v, (blk.nq_w, blk.nq_b), (blk.nk_w, blk.nk_b),
-                     1e-6, rope, St, k2_out=k2, v2_out=v2, mask2=resample_mask_u8)
-        ops.attention(ws.q, ws.k, ws.v, ws.ao, B, H, S, S, scale, k1=k2, v1=v2, kv_len1=S)
+        ops.attention(ws.q, ws.k, ws.v, ws.ao, B, Hl, S, S, scale, k1=k2, v1=v2, kv_len1=S, ldo=ldo)
     else:
-        ops.gemm_qkv(ws.xn, blk.qkv_w, blk.qkv_b, M, D, S, H, 0, ws.q, ws.k, ws.v, (blk.nq_w, blk.nq_b), (blk.nk_w, blk.nk_b),
-                     1e-6, rope, St, )
+        _qkv(pm, blk, ws, ws.xn, 0, rope, group=group)
         if use_prev:
             # T3D:141-146: norm1 of the previous window's states with the current timestep embedding
+            ops.ln_modulate(prev, R, 0, ws.xn, B, R, D, blk.n1_w, blk.n1_b, d.eps, ws.mod1, OFF1, St)
             k2, v2 = ws.second_kv()
-            ops.ln_modulate(prev, S, 0, ws.xn, B, S, D, blk.n1_w, blk.n1_b, d.eps, ws.mod1, OFF1, St)
-            kv_w = blk.qkv_w[D:]
-            kv_b = blk.qkv_b[D:]
             if d.resample:                                            # AP:2247-2252, one softmax over 2S keys
-                ops.gemm_qkv(ws.xn, kv_w, kv_b, M, D, S, H, 1, None, k2, v2, None, (blk.nk_w, blk.nk_b), 1e-6, rope, St,
-                             row_scale=prev_mask)
-                ops.attention(ws.q, ws.k, ws.v, ws.ao, B, H, S, S, scale, k1=k2, v1=v2, kv_len1=S)
+                _qkv(pm, blk, ws, ws.xn, 1, rope, row_scale=prev_mask, group=group)
+                ops.attention(ws.q, ws.k, ws.v, ws.ao, B, Hl, S, S, scale, k1=k2, v1=v2, kv_len1=S, ldo=ldo)
             else:                                                     # AP:2156-2189, blend of two attentions
-                ops.gemm_qkv(ws.xn, kv_w, kv_b, M, D, S, H, 1, None, k2, v2, None, (blk.nk_w, blk.nk_b), 1e-6, rope, St)
-                ops.attention(ws.q, ws.k, ws.v, ws.ao, B, H, S, S, scale, out_scale=1.0 - prev_w)
-                ops.attention(ws.q, k2, v2, ws.ao, B, H, S, S, scale, out_scale=prev_w, accumulate=True)
+                _qkv(pm, blk, ws, ws.xn, 1, rope, group=group)
+                ops.attention(ws.q, ws.k, ws.v, ws.ao, B, Hl, S, S, scale, out_scale=1.0 - prev_w, ldo=ldo)
+                ops.attention(ws.q, k2, v2, ws.ao, B, Hl, S, S, scale, out_scale=prev_w, accumulate=True, ldo=ldo)
         else:
-            ops.attention(ws.q, ws.k, ws.v, ws.ao, B, H, S, S, scale)
+            ops.attention(ws.q, ws.k, ws.v, ws.ao, B, Hl, S, S, scale, ldo=ldo)
     # to_out + gated residual (AP:2202, T3D:169-170): gate = chunk 2 (video) / 5 (text)
-    ops.gemm_gate_residual(ws.ao, blk.out_w, blk.out_b, ws.xmid, M, D, D, rows_per_batch=S, out_batch_rows=S, out_row_offset=0,
-                           res=x_in, res_batch_rows=S, res_row_offset=0, gate=ws.mod1, gate_video_off=2 * D,
-                           gate_text_off=5 * D, text_len=St)
+    a_kw = {}
+    ao = ws.ao
+    if sh.sp > 1:                                                      # heads gathered from the peers: [peer][row][Hl * 64]
+        group.all_to_all(ws.ao_recv, ws.ao)
+        ao = ws.ao_recv
+        a_kw = dict(lda=ldo, a_k_chunk=ldo, a_chunk_stride=R * ldo)
+    ops.gemm_gate_residual(ao, blk.out_w, blk.out_b, ws.xmid, M, D, D, rows_per_batch=R, out_batch_rows=R, out_row_offset=0,
+                           res=x_in, res_batch_rows=R, res_row_offset=0, gate=ws.mod1, gate_video_off=2 * D,
+                           gate_text_off=5 * D, text_len=St, **a_kw)
     ops.gemv(emb, blk.n2_lin_w, blk.n2_lin_b, act_silu=True, out=ws.mod2)
-    ops.ln_modulate(ws.xmid, S, 0, ws.xn, B, S, D, blk.n2_w, blk.n2_b, d.eps, ws.mod2, OFF1, St)
+    ops.ln_modulate(ws.xmid, R, 0, ws.xn, B, R, D, blk.n2_w, blk.n2_b, d.eps, ws.mod2, OFF1, St)
     ops.gemm_gelu(ws.xn, blk.ff1_w, blk.ff1_b, ws.ffm, M, 4 * D, D)
     inj_kw = {}
     if inject is not None:
         inj_kw = dict(inject=inject, inject_batch_stride=inject.stride(0), ldi=inject.stride(1), inject_mask=inject_mask,
                       video_len=Sv)
-    ops.gemm_gate_residual(ws.ffm, blk.ff2_w, blk.ff2_b, x_out, M, D, 4 * D, rows_per_batch=S, out_batch_rows=S, out_row_offset=0,
-                           res=ws.xmid, res_batch_rows=S, res_row_offset=0, gate=ws.mod2, gate_video_off=2 * D,
+    ops.gemm_gate_residual(ws.ffm, blk.ff2_w, blk.ff2_b, x_out, M, D, 4 * D, rows_per_batch=R, out_batch_rows=R, out_row_offset=0,
+                           res=ws.xmid, res_batch_rows=R, res_row_offset=0, gate=ws.mod2, gate_video_off=2 * D,
                            gate_text_off=5 * D, text_len=St, **inj_kw)
 
 
-def _prep_rope(rope, device, Sv):
+def _prep_rope(rope, device, Sv, sh: Optional[Shard] = None):
+    """(cos, sin) fp32 [Sv, 64] on the device; for a shard, the rows of its own video tokens (row s - text_rows of the
+    returned tables belongs to owned row s)."""
     if rope is None:
         return None
     cos, sin = rope
@@ -278,6 +354,8 @@ def _prep_rope(rope, device, Sv):
     sin = sin.to(device=device, dtype=torch.float32).contiguous()
     if cos.shape != (Sv, 64) or sin.shape != (Sv, 64):
         raise ValueError(f"image_rotary_emb must be two [{Sv}, 64] tables, got {tuple(cos.shape)}")
+    if sh is not None and sh.sp > 1:
+        cos, sin = cos[sh.video0:], sin[sh.video0:]
     return cos, sin
 
 
@@ -291,15 +369,27 @@ def _check_inputs(pm: PackedModel, hidden_states, encoder_hidden_states):
         raise ValueError(f"encoder_hidden_states must be [B, {d.max_text}, {d.text_dim}]")
 
 
+def _layout(pm: PackedModel, B_global: int, S: int, St: int):
+    """(runtime, batch slice, local batch, shard) of this call: the CFG batch splits over the CFG groups, the sequence over
+    the ranks of a group (parallel.py); a single GPU owns everything."""
+    rt = parallel.current()
+    if rt is None:
+        return None, slice(0, B_global), B_global, Shard(1, 0, S, St, pm.dims.heads)
+    plan = rt.plan
+    return rt, plan.batch_slice(B_global), plan.local_batch(B_global), rt.shard(S, St, pm.dims.heads)
+
+
 @torch.no_grad()
 def branch_forward(pm: PackedModel, hidden_states: torch.Tensor, encoder_hidden_states: torch.Tensor, branch_cond: torch.Tensor,
                    timestep, image_rotary_emb, conditioning_scale: float = 1.0) -> List[torch.Tensor]:
-    """CogvideoXBranchModel.forward BR:295-434 (wo_text = False)."""
+    """CogvideoXBranchModel.forward BR:295-434 (wo_text = False).  On several GPUs every rank is given the whole CFG batch and
+    returns the block samples of ITS sample and ITS video rows ([B_local, owned video rows, D]); transformer_forward on the
+    same rank consumes exactly that."""
     _check_inputs(pm, hidden_states, encoder_hidden_states)
     d = pm.dims
     dtype = hidden_states.dtype
     dev = hidden_states.device
-    B, Fr, C, H, W = hidden_states.shape
+    Bg, Fr, C, H, W = hidden_states.shape
     if C + branch_cond.shape[2] != d.patch_in_channels:
         raise ValueError(f"branch expects {d.patch_in_channels} conditioning channels, got {C} + {branch_cond.shape[2]}")
     Sv = Fr * (H // d.patch) * (W // d.patch)
@@ -307,20 +397,25 @@ def branch_forward(pm: PackedModel, hidden_states: torch.Tensor, encoder_hidden_
     S = St + Sv
     if pm.pos.shape[0] != S:
         raise ValueError("resolution / frame count must match the learned positional table (EMB:433-437)")
-    ws = _workspace(pm, B, S, Sv, dev)
+    rt, bs, B, sh = _layout(pm, Bg, S, St)
+    group = rt                                                        # collectives of this rank (None on one GPU)
+    if torch.is_tensor(timestep) and timestep.ndim > 0 and timestep.shape[0] == Bg:
+        timestep = timestep[bs]
+    ws = _workspace(pm, B, S, Sv, sh, dev)
     emb = _time_embedding(pm, timestep, B, dev)
-    rope = _prep_rope(image_rotary_emb, dev, Sv)
-    x = [torch.empty(B, S, d.D, dtype=BF16, device=dev) for _ in range(d.num_layers + 1)]
-    _embed(pm, ws, x[0], encoder_hidden_states.to(BF16).contiguous(), hidden_states.to(BF16).contiguous(),
-           branch_cond.to(BF16).contiguous(), B, Fr, H, W, St, Sv)
+    rope = _prep_rope(image_rotary_emb, dev, Sv, sh)
+    R = sh.rows
+    x = [torch.empty(B, R, d.D, dtype=BF16, device=dev) for _ in range(d.num_layers + 1)]
+    _embed_sharded(pm, ws, x[0], encoder_hidden_states[bs].to(BF16).contiguous(), hidden_states[bs].to(BF16).contiguous(),
+                   branch_cond[bs].to(BF16).contiguous(), B, Fr, H, W, St, Sv)
     outs = []
     for i, blk in enumerate(pm.blocks):
-        _block(pm, blk, ws, x[i], x[i + 1], emb, rope, B, S, St, Sv)
+        _block(pm, blk, ws, x[i], x[i + 1], emb, rope, B, S, sh.text_rows, sh.video_rows, group=group)
     for i in range(d.num_layers):
-        o = torch.empty(B, Sv, d.D, dtype=BF16, device=dev)
+        o = torch.empty(B, sh.video_rows, d.D, dtype=BF16, device=dev)
         # branch_blocks[i] on the video rows only (BR:416-421); text rows are dropped by the negative row offset
-        ops.gemm_bias(x[i + 1], pm.branch_w[i], pm.branch_b[i], o, B * S, d.D, d.D, rows_per_batch=S, out_batch_rows=Sv,
-                      out_row_offset=-St, alpha=float(conditioning_scale))
+        ops.gemm_bias(x[i + 1], pm.branch_w[i], pm.branch_b[i], o, B * R, d.D, d.D, rows_per_batch=R, out_batch_rows=sh.video_rows,
+                      out_row_offset=-sh.text_rows, alpha=float(conditioning_scale))
         outs.append(o.to(dtype))
     return outs
 
@@ -332,12 +427,15 @@ def transformer_forward(pm: PackedModel, hidden_states: torch.Tensor, encoder_hi
                         branch_block_masks: Optional[torch.Tensor] = None, add_first: bool = False,
                         return_hidden_states: bool = False, return_resample_mask: bool = False,
                         id_pool_resample_learnable: bool = False):
-    """CogVideoXTransformer3DModel.forward T3D:472-646; returns (output, hidden_states_list | None, resample_mask | None)."""
+    """CogVideoXTransformer3DModel.forward T3D:472-646; returns (output, hidden_states_list | None, resample_mask | None).
+    On several GPUs: every rank is given the whole CFG batch, computes its sample / its rows, and returns the complete
+    noise prediction [B, F, C, H, W] (gathered) and resample mask; the hidden-state list (and the `prev_hidden_states` it
+    feeds on the next window) stays sharded: entries are [B_local, owned rows, D]."""
     _check_inputs(pm, hidden_states, encoder_hidden_states)
     d = pm.dims
     dtype = hidden_states.dtype
     dev = hidden_states.device
-    B, Fr, C, H, W = hidden_states.shape
+    Bg, Fr, C, H, W = hidden_states.shape
     if C != d.patch_in_channels:
         raise ValueError(f"transformer expects {d.patch_in_channels} latent channels, got {C}")
     Sv = Fr * (H // d.patch) * (W // d.patch)
@@ -347,24 +445,34 @@ def transformer_forward(pm: PackedModel, hidden_states: torch.Tensor, encoder_hi
     if pm.pos.shape[0] != S:
         raise ValueError("resolution / frame count must match the learned positional table (EMB:433-437)")
     L = d.num_layers
-    ws = _workspace(pm, B, S, Sv, dev)
+    rt, bs, B, sh = _layout(pm, Bg, S, St)
+    group = rt                                                        # collectives of this rank (None on one GPU)
+    R, St_l, Sv_l = sh.rows, sh.text_rows, sh.video_rows
+    if torch.is_tensor(timestep) and timestep.ndim > 0 and timestep.shape[0] == Bg:
+        timestep = timestep[bs]
+    ws = _workspace(pm, B, S, Sv, sh, dev)
     emb = _time_embedding(pm, timestep, B, dev)
-    rope = _prep_rope(image_rotary_emb, dev, Sv)
+    rope = _prep_rope(image_rotary_emb, dev, Sv, sh)
 
-    mask_u8 = None
+    # masks are tiny: every rank pools the whole batch (the returned resample mask is global), kernels get local slices
+    mask_all = None
     if branch_block_masks is not None:
-        mask_u8 = torch.empty(B, Sv, dtype=torch.uint8, device=dev)
-        ops.mask_pool(branch_block_masks.to(BF16).contiguous(), mask_u8, B * Fr, H, W)
+        mask_all = torch.empty(Bg, Sv, dtype=torch.uint8, device=dev)
+        ops.mask_pool(branch_block_masks.to(BF16).contiguous(), mask_all, Bg * Fr, H, W)
     resample_mask = None
-    rm_u8 = None
+    rm_local = None
     if id_pool_resample_learnable or return_resample_mask:
-        if mask_u8 is None:
+        if mask_all is None:
             raise ValueError("id_pool_resample needs masks")                      # T3D:536-537
-        rm_u8 = torch.zeros(B, S, dtype=torch.uint8, device=dev)
-        rm_u8[:, St:] = mask_u8
+        rm_u8 = torch.zeros(Bg, S, dtype=torch.uint8, device=dev)
+        rm_u8[:, St:] = mask_all
         resample_mask = rm_u8.bool()
-    if d.resample and rm_u8 is None:
+        rm_local = rm_u8[bs, sh.row0:sh.row0 + R].contiguous().reshape(-1)
+    if d.resample and rm_local is None:
         raise ValueError("the ID-resample attention processor needs branch_block_masks (T3D:534-543)")
+    mask_local = None
+    if mask_all is not None:
+        mask_local = mask_all[bs, sh.video0:sh.video0 + Sv_l].contiguous()
 
     kw = dict(attention_kwargs) if attention_kwargs else {}
     kw.pop("scale", None)      # LoRA scale: adapters are merged at pack time
@@ -375,25 +483,30 @@ def transformer_forward(pm: PackedModel, hidden_states: torch.Tensor, encoder_hi
         pmk = kw.get("prev_resample_mask")
         if pmk is None:
             raise ValueError("prev_resample_mask is required with prev_hidden_states on the ID-resample processor")
-        prev_mask_f = (pmk.to(device=dev, dtype=torch.float32) * float(prev_w)).reshape(-1).contiguous()
+        pmk = pmk.to(device=dev, dtype=torch.float32)[bs, sh.row0:sh.row0 + R]
+        prev_mask_f = (pmk * float(prev_w)).reshape(-1).contiguous()
 
     if return_hidden_states:
-        arena = torch.empty(L + 1, B, S, D, dtype=BF16, device=dev)
+        arena = torch.empty(L + 1, B, R, D, dtype=BF16, device=dev)
         xs = [arena[i] for i in range(L + 1)]
     else:
         if ws.ping[0] is None:
-            ws.ping = [torch.empty(B, S, D, dtype=BF16, device=dev) for _ in range(2)]
+            ws.ping = [torch.empty(B, R, D, dtype=BF16, device=dev) for _ in range(2)]
         xs = [ws.ping[i % 2] for i in range(L + 1)]
 
-    _embed(pm, ws, xs[0], encoder_hidden_states.to(BF16).contiguous(), hidden_states.to(BF16).contiguous(), None,
-           B, Fr, H, W, St, Sv)
+    _embed_sharded(pm, ws, xs[0], encoder_hidden_states[bs].to(BF16).contiguous(), hidden_states[bs].to(BF16).contiguous(), None,
+                   B, Fr, H, W, St, Sv)
 
     samples = None
     if branch_block_samples is not None:
         samples = []
         for s in branch_block_samples:
             s = s.to(BF16)
-            if s.stride(-1) != 1 or s.shape != (B, Sv, D):
+            if rt is not None and s.shape == (Bg, Sv, D):            # full samples (e.g. from a reference branch): take our part
+                s = s[bs, sh.video0:sh.video0 + Sv_l]
+            if s.shape != (B, Sv_l, D):
+                raise ValueError(f"branch_block_samples must be [{B}, {Sv_l}, {D}] on this rank, got {tuple(s.shape)}")
+            if s.stride(-1) != 1:
                 s = s.contiguous()
             samples.append(s)
     interval = int(math.ceil(L / len(samples))) if samples else 1                  # T3D:598-599
@@ -409,19 +522,35 @@ def transformer_forward(pm: PackedModel, hidden_states: torch.Tensor, encoder_hi
         if prev_states is not None:
             prev = prev_states.get(i)                                              # T3D:574-582
             if prev is not None:
-                prev = prev.to(device=dev, dtype=BF16).contiguous()
-        _block(pm, blk, ws, xs[i], xs[i + 1], emb, rope, B, S, St, Sv, resample_mask_u8=None if rm_u8 is None else rm_u8.reshape(-1),
+                prev = prev.to(device=dev, dtype=BF16)
+                if rt is not None and prev.shape == (Bg, S, D):
+                    prev = prev[bs, sh.row0:sh.row0 + R]
+                prev = prev.contiguous()
+        _block(pm, blk, ws, xs[i], xs[i + 1], emb, rope, B, S, St_l, Sv_l, resample_mask_u8=rm_local,
                prev=prev, prev_w=prev_w if prev is not None else None, prev_mask=prev_mask_f, inject=inject,
-               inject_mask=mask_u8 if inject is not None else None)
+               inject_mask=mask_local if inject is not None else None, group=group)
 
     # final head T3D:613-632
     mod = ops.gemv(emb, pm.no_lin_w, pm.no_lin_b, act_silu=True)                   # [B, 2D]: shift | scale (NRM:78)
-    xf = ws.xn[: B * Sv]
-    ops.ln_final(xs[L], S, St, xf, B, Sv, D, pm.nf_w, pm.nf_b, pm.no_w, pm.no_b, d.eps, mod, 0, D)
     n_out = d.patch * d.patch * d.out_channels
-    po = ws.ao.view(-1)[: B * Sv * n_out].view(B * Sv, n_out)
-    ops.gemm_bias(xf, pm.proj_w, pm.proj_b, po, B * Sv, n_out, D, rows_per_batch=B * Sv, out_batch_rows=0, out_row_offset=0)
-    out = torch.empty(B, Fr, d.out_channels, H, W, dtype=BF16, device=dev)
-    ops.unpatchify(po, out, B * Fr, d.out_channels, H, W)
+    out = torch.empty(Bg, Fr, d.out_channels, H, W, dtype=BF16, device=dev)
+    xf = ws.xn[: B * Sv_l]
+    if Sv_l > 0:
+        ops.ln_final(xs[L], R, St_l, xf, B, Sv_l, D, pm.nf_w, pm.nf_b, pm.no_w, pm.no_b, d.eps, mod, 0, D)
+    if rt is None:
+        po = ws.ao.view(-1)[: B * Sv * n_out].view(B * Sv, n_out)
+        ops.gemm_bias(xf, pm.proj_w, pm.proj_b, po, B * Sv, n_out, D, rows_per_batch=B * Sv, out_batch_rows=0, out_row_offset=0)
+        ops.unpatchify(po, out, B * Fr, d.out_channels, H, W)
+    else:
+        # every rank projects its video rows into its [R, n_out] slot of the joint layout, one all-gather over the whole
+        # world assembles [B_global, S, n_out] on every rank (2.2 MB per sample), text rows are skipped when unpatchifying
+        slot = torch.zeros(B, R, n_out, dtype=BF16, device=dev)
+        if Sv_l > 0:
+            ops.gemm_bias(xf, pm.proj_w, pm.proj_b, slot, B * Sv_l, n_out, D, rows_per_batch=Sv_l, out_batch_rows=R,
+                          out_row_offset=St_l)
+        joint = torch.empty(Bg, S, n_out, dtype=BF16, device=dev)
+        rt.all_gather(joint, slot)
+        for b in range(Bg):
+            ops.unpatchify(joint[b, St:], out[b], Fr, d.out_channels, H, W)
     hs_list = [xs[i + 1] for i in range(L)] if return_hidden_states else None
     return out.to(dtype), hs_list, resample_mask

@@ -59,6 +59,15 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+def _base(t: Optional[torch.Tensor], dtype=BF16) -> Optional[int]:
+    """Base address of a CUDA tensor that the kernel indexes with its own strides (views into larger buffers)."""
+    if t is None:
+        return None
+    if not t.is_cuda or t.dtype != dtype:
+        raise RuntimeError(f"expected a CUDA {dtype} tensor (the B200 path has no CPU fallback)")
+    return t.data_ptr()
+
+
 def _p(t: Optional[torch.Tensor], dtype=None, name: str = "tensor") -> Optional[int]:
     if t is None:
         return None
@@ -133,26 +142,39 @@ def gemm_gelu(a, w, bias, out, m, n, k):
 @_timed('gemm_gate_residual', _gemm_flops)
 def gemm_gate_residual(a, w, bias, out, m, n, k, rows_per_batch, out_batch_rows, out_row_offset, res, res_batch_rows,
                        res_row_offset, gate=None, gate_video_off=0, gate_text_off=0, text_len=0, inject=None,
-                       inject_batch_stride=0, ldi=0, inject_mask=None, video_len=0, lda=None, ldw=None):
+                       inject_batch_stride=0, ldi=0, inject_mask=None, video_len=0, lda=None, ldw=None, a_k_chunk=0,
+                       a_chunk_stride=0):
     check(lib().vp_gemm_gate_residual(
         _p(a, BF16, "gemm.a"), lda or k, _p(w, BF16, "gemm.w"), ldw or k, _p(bias, BF16, "gemm.bias"), _p(out, BF16, "gemm.out"),
         n, m, n, k, rows_per_batch, out_batch_rows, out_row_offset, _p(res, BF16, "gemm.res"), n, res_batch_rows, res_row_offset,
         _p(gate, torch.float32, "gemm.gate"), 0 if gate is None else gate.shape[1], gate_video_off, gate_text_off, text_len,
         None if inject is None else inject.data_ptr(), inject_batch_stride, ldi,
-        _p(inject_mask, torch.uint8, "gemm.inject_mask"), video_len, _stream()), "vp_gemm_gate_residual")
+        _p(inject_mask, torch.uint8, "gemm.inject_mask"), video_len, a_k_chunk, a_chunk_stride, _stream()),
+        "vp_gemm_gate_residual")
     return out
 
 
 @_timed('gemm_qkv', lambda a, w, bias, m, k, batch_rows, heads, qkv_first, *r, **kw: 2.0 * m * k * (3 - qkv_first) * heads * 64)
 def gemm_qkv(a, w, bias, m, k, batch_rows, heads, qkv_first, q_out, k_out, v_out, norm_q, norm_k, qk_eps, rope, text_len,
-             k2_out=None, v2_out=None, mask2=None, row_scale=None, ldw=None):
+             k2_out=None, v2_out=None, mask2=None, row_scale=None, ldw=None, heads_per_dest=None, dest_stride=0):
+    """heads_per_dest / dest_stride: Ulysses send layout (include/vp_b200.h); q_out .. v2_out may then be views into one send
+    buffer, so only their base addresses are taken."""
     cos, sin = (None, None) if rope is None else rope
     check(lib().vp_gemm_qkv(
         _p(a, BF16, "qkv.a"), k, _p(w, BF16, "qkv.w") if w.is_contiguous() else w.data_ptr(), ldw or k, _p(bias, BF16, "qkv.bias"),
-        m, k, batch_rows, heads, qkv_first, _p(q_out, BF16), _p(k_out, BF16), _p(v_out, BF16), _p(k2_out, BF16), _p(v2_out, BF16),
+        m, k, batch_rows, heads, qkv_first, _base(q_out), _base(k_out), _base(v_out), _base(k2_out), _base(v2_out),
         _p(mask2, torch.uint8, "qkv.mask2"), _p(row_scale, torch.float32, "qkv.row_scale"),
         _p(norm_q[0], BF16) if norm_q else None, _p(norm_q[1], BF16) if norm_q else None, _p(norm_k[0], BF16), _p(norm_k[1], BF16),
-        float(qk_eps), _p(cos, torch.float32, "rope.cos"), _p(sin, torch.float32, "rope.sin"), text_len, _stream()), "vp_gemm_qkv")
+        float(qk_eps), _base(cos, torch.float32), _base(sin, torch.float32), text_len, heads_per_dest or heads, dest_stride,
+        _stream()), "vp_gemm_qkv")
+
+
+@_timed('a2a_unpack', lambda src, dsts, peers, heads_local, rows_per_peer: 4.0 * len(dsts) * peers * heads_local * rows_per_peer * 64)
+def a2a_unpack_heads(src, dsts, peers, heads_local, rows_per_peer):
+    """src [peers][len(dsts)][heads_local][rows_per_peer][64] -> dsts[i] [heads_local][peers * rows_per_peer][64]."""
+    ptrs = [_p(d, BF16, "unpack.dst") for d in dsts] + [None] * (5 - len(dsts))
+    check(lib().vp_a2a_unpack_heads(_p(src, BF16, "unpack.src"), *ptrs, len(dsts), peers, heads_local, rows_per_peer, _stream()),
+          "vp_a2a_unpack_heads")
 
 
 @_timed('attention', lambda q, k0, v0, out, batch, heads, seq_q, kv_len0, scale, k1=None, v1=None, kv_len1=0, **kw: 4.0 * batch * heads * seq_q * (kv_len0 + kv_len1) * 64)

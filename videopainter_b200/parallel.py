@@ -2,16 +2,24 @@
 
 The step has two independent halves — the CFG batch (uncond, cond: PIPE:937-942) — and, inside each half, token-wise
 work that shards freely plus one all-to-all pair around every attention (Ulysses).  Layout for N ranks:
-    cfg_groups = 2 (N >= 2): ranks [0, N/2) run the uncond sample, ranks [N/2, N) the cond sample, no traffic between the
-                 halves except the final noise-pred exchange;
-    sp = N / cfg_groups ranks per half share the sequence (Ulysses) when N >= 4.
+    cfg_groups = 2 (N >= 2): ranks [0, N/2) run the uncond sample, ranks [N/2, N) the cond sample; no traffic between
+                 the halves except the final noise-pred gather (2.2 MB per sample);
+    sp = N / cfg_groups ranks per half share the joint (text ‖ video) sequence: rank r owns rows [r S/sp, (r+1) S/sp).
+                 Before attention the QKV GEMM epilogue has already written each destination rank's heads into its own
+                 contiguous send block, an all-to-all turns [S/sp, H] into [S, H/sp], attention runs on H/sp heads over
+                 the whole sequence, and a second all-to-all returns the output to token sharding, where the out-projection
+                 GEMM reads it straight from the receive buffer (K-chunked A operand) — no pack / unpack pass on that side.
+
+Everything here is host-side index arithmetic plus process-group handles; it runs (and is tested) on CPU with gloo.
 """
 from __future__ import annotations
 
+import threading
 from dataclasses import dataclass
+from typing import Optional, Tuple
 
 
-@dataclass
+@dataclass(frozen=True)
 class Plan:
     world: int
     rank: int
@@ -26,10 +34,19 @@ class Plan:
     def sp_rank(self) -> int:
         return self.rank % self.sp
 
+    def sp_ranks(self) -> Tuple[int, ...]:
+        """Global ranks of this rank's sequence-parallel group (same CFG half)."""
+        base = self.cfg_index * self.sp
+        return tuple(range(base, base + self.sp))
+
     def local_batch(self, global_batch: int) -> int:
         if global_batch % self.cfg_groups:
-            raise ValueError("CFG batch must divide over the CFG groups")
+            raise ValueError(f"batch {global_batch} does not divide over {self.cfg_groups} CFG groups")
         return global_batch // self.cfg_groups
+
+    def batch_slice(self, global_batch: int) -> slice:
+        b = self.local_batch(global_batch)
+        return slice(self.cfg_index * b, (self.cfg_index + 1) * b)
 
     def describe(self) -> str:
         if self.world == 1:
@@ -40,8 +57,125 @@ class Plan:
 def make_plan(world: int, rank: int) -> Plan:
     if world < 1 or (world & (world - 1)):
         raise ValueError("world size must be a power of two")
+    if not 0 <= rank < world:
+        raise ValueError("rank out of range")
     cfg_groups = 2 if world >= 2 else 1
-    sp = world // cfg_groups
-    if sp > 1:
-        raise NotImplementedError("Ulysses sequence parallelism (sp > 1) is not wired into the engine yet")
-    return Plan(world=world, rank=rank, cfg_groups=cfg_groups, sp=sp)
+    return Plan(world=world, rank=rank, cfg_groups=cfg_groups, sp=world // cfg_groups)
+
+
+@dataclass(frozen=True)
+class Shard:
+    """Rows of the joint (text ‖ video) sequence owned by one sequence-parallel rank."""
+    sp: int             # ranks sharing the sequence
+    sp_rank: int
+    seq: int            # S = text + video rows
+    text: int           # text rows in the whole sequence (they come first: AP:2121)
+    heads: int
+
+    def __post_init__(self):
+        if self.seq % self.sp:
+            raise ValueError(f"sequence length {self.seq} does not divide over {self.sp} ranks")
+        if self.heads % self.sp:
+            raise ValueError(f"{self.heads} heads do not divide over {self.sp} ranks")
+
+    @property
+    def rows(self) -> int:              # rows owned by this rank
+        return self.seq // self.sp
+
+    @property
+    def row0(self) -> int:              # first owned row
+        return self.sp_rank * self.rows
+
+    @property
+    def text_rows(self) -> int:         # owned rows that are text tokens (all of them sit on the first ranks)
+        return min(max(self.text - self.row0, 0), self.rows)
+
+    @property
+    def video_rows(self) -> int:
+        return self.rows - self.text_rows
+
+    @property
+    def video0(self) -> int:            # index of the first owned video row among the video rows
+        return max(self.row0 - self.text, 0)
+
+    @property
+    def heads_local(self) -> int:
+        return self.heads // self.sp
+
+
+class Runtime:
+    """Process-group handles of one rank.  `world_group` spans every rank (final gather), `sp_group` the ranks that share
+    this rank's sequence (the per-attention all-to-alls)."""
+
+    def __init__(self, plan: Plan, sp_group=None, world_group=None):
+        self.plan = plan
+        self.sp_group = sp_group
+        self.world_group = world_group
+
+    def shard(self, seq: int, text: int, heads: int) -> Shard:
+        return Shard(self.plan.sp, self.plan.sp_rank, seq, text, heads)
+
+    # The two collectives of the data path.  Both enqueue NCCL work ordered after the caller's current CUDA stream and
+    # make that stream wait for the result; the host does not block.
+    def all_to_all(self, out, inp) -> None:
+        """Equal-split all-to-all over the sequence-parallel group: chunk d of `inp` goes to peer d, chunk s of `out`
+        comes from peer s."""
+        import torch.distributed as dist
+        dist.all_to_all_single(out.view(-1), inp.view(-1), group=self.sp_group)
+
+    def all_gather(self, out, inp) -> None:
+        """`out` = concatenation over all ranks (rank order) of `inp`."""
+        import torch.distributed as dist
+        dist.all_gather_into_tensor(out.view(-1), inp.view(-1), group=self.world_group)
+
+
+_tls = threading.local()      # per thread, so that tests can run several virtual ranks of one process side by side
+
+
+def init(world: Optional[int] = None, rank: Optional[int] = None) -> Runtime:
+    """Build the plan and the process groups from an initialised torch.distributed (call after init_process_group).
+    Every rank must call this (new_group is collective)."""
+    import torch.distributed as dist
+    if world is None:
+        world = dist.get_world_size() if dist.is_initialized() else 1
+        rank = dist.get_rank() if dist.is_initialized() else 0
+    plan = make_plan(world, rank)
+    sp_group = None
+    if world > 1:
+        for g in range(plan.cfg_groups):                      # every rank creates every group, in the same order
+            ranks = list(range(g * plan.sp, (g + 1) * plan.sp))
+            grp = dist.new_group(ranks) if plan.sp > 1 else None
+            if g == plan.cfg_index:
+                sp_group = grp
+    return install(Runtime(plan, sp_group, None))
+
+
+def install(rt: Optional[Runtime]) -> Optional[Runtime]:
+    """Make `rt` the runtime of the calling thread (None = single GPU)."""
+    _tls.runtime = rt
+    return rt
+
+
+def shutdown() -> None:
+    _tls.runtime = None
+
+
+def current() -> Optional[Runtime]:
+    """The runtime installed by init() / install() on this thread, or None on a single GPU."""
+    rt = getattr(_tls, "runtime", None)
+    if rt is not None and rt.plan.world > 1:
+        return rt
+    return None
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# layout arithmetic shared with the kernels (include/vp_b200.h: vp_gemm_qkv heads_per_dest / vp_a2a_unpack_heads)
+# ----------------------------------------------------------------------------------------------------------------------
+def send_block_shape(sh: Shard, slots: int) -> Tuple[int, int, int, int, int]:
+    """Shape of the QKV send buffer: [destination rank][slot (q, k, v, ...)][head within destination][owned row][64]."""
+    return (sh.sp, slots, sh.heads_local, sh.rows, 64)
+
+
+def qkv_dest_stride(sh: Shard, slots: int) -> int:
+    """Elements between two destinations' blocks of the send buffer."""
+    return slots * sh.heads_local * sh.rows * 64
