@@ -288,8 +288,9 @@ def main() -> None:
                       "parallelism": plan.describe(), "l2": "per-step working set (11.7 GB weights, 218 MB activations per "
                       "layer) exceeds the 126 MB L2; no explicit flush", "random_init": True},
            "step_tflops": flops / (ms_per_step * 1e-3) / 1e12,
-           "frac_of_bf16_peak": {"sustained": flops / (ms_per_step * 1e-3) / 1e12 / peak_tf,
-                                 "burst": flops / (ms_per_step * 1e-3) / 1e12 / peaks.get("bf16_tflops", 1650.0)},
+           "frac_of_bf16_peak": {"sustained": flops / (ms_per_step * 1e-3) / 1e12 / (peak_tf * world),
+                                 "burst": flops / (ms_per_step * 1e-3) / 1e12 / (peaks.get("bf16_tflops", 1650.0) * world),
+                                 "note": "whole-job algorithmic FLOP/s over n_gpus x the measured cuBLAS peak"},
            "roofline": roofline, "clocks": clocks, "gpu_launches": launches,
            "e2e": {"value": 1000.0 / e2e_ms, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                    "ms_per_step": e2e_ms}}
