@@ -71,6 +71,8 @@ def main():
     gam = rn(D)
     timeit("ln_modulate", lambda: ops.ln_modulate(x, S, 0, xo, B, S, D, gam, gam, 1e-5, gate, (0, D, 3 * D, 4 * D), St),
            4.0 * M * D, "gbs")
+    x3 = x.view(B, S, D)
+    timeit("ln_modulate_copy_for_scale", lambda: xo.copy_(x3), 4.0 * M * D, "gbs")   # same bytes moved by a plain device copy
     # the library GEMM / SDPA of this box, for scale only (not part of the product path)
     wt = w1.t().contiguous()
     timeit("cublas_ff1_for_scale", lambda: torch.matmul(x, wt), 2.0 * M * 4 * D * D, "tflops")

@@ -27,78 +27,165 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// LayerNorm + expert modulation.  One warp per token row; the row lives in registers (CH chunks of 8 bf16 per lane),
-// statistics in fp32 (two-pass on registers), 16-byte loads and stores, text/video expert selected per row.
-//   y = LN(x; gamma, beta, eps) * (1 + scale[b, e]) + shift[b, e]        e = text if s < text_len else video
+// LayerNorm + expert modulation:  y = LN(x; gamma, beta, eps) * (1 + scale[b, e]) + shift[b, e],  e = text if s < text_len
+// else video.  HBM-bound (read + write of [rows, D] bf16), so the kernel is organised around memory traffic:
+//  * thread t owns columns [8t, 8t + 8) of EVERY row its CTA touches, hence the per-column coefficients
+//      A = gamma (1 + scale),  C = beta (1 + scale) + shift      (fp32, one pair per (batch, expert))
+//    sit in 16 registers (the earlier warp-per-row version re-read 36 KB of parameters per 6 KB row through L1 and was
+//    LSU-bound at 47 % of the HBM roofline);
+//  * persistent CTAs walk units of LN_RB consecutive rows of one (batch, expert) segment; a unit is one contiguous
+//    block of x, fetched by a single bulk async copy (cp.async.bulk -> mbarrier) into a shared-memory ring LN_STAGES
+//    deep, so ~100 KB per CTA are in flight without costing registers (HBM latency under load is ~2 us);
+//  * row statistics are fp32, two-pass on registers, reduced warp-shuffle -> shared memory -> one warp per row;
+//    results leave with 16-byte stores straight from registers.
 // ------------------------------------------------------------------------------------------------------------------
-template <int CH>
-__global__ void __launch_bounds__(256, (CH <= 8 ? 3 : (CH <= 12 ? 2 : 1))) ln_modulate_kernel(const LnModParams p) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * 8 + warp;
-  if (row >= p.rows) return;
-  const int b = (int)(row / p.rows_per_batch);
-  const int s = (int)(row - (long long)b * p.rows_per_batch);
-  const __nv_bfloat16* x = p.x + ((long long)b * p.x_batch_rows + p.x_row_offset + s) * p.D;
-  __nv_bfloat16* y = p.y + row * p.D;
-  const int nchunk = p.D >> 3;   // 8-element chunks in the row
+#ifndef VP_LN_RB
+#define VP_LN_RB 4
+#define VP_LN_CTAS 2
+#endif
+constexpr int LN_RB = VP_LN_RB;          // rows per unit
+constexpr int LN_CTAS = VP_LN_CTAS;      // resident CTAs per SM the register / shared-memory budget is set for
+constexpr int LN_MAX_WARPS = 16;         // D <= 4096
+constexpr int LN_MAX_STAGES = 6;
+constexpr int LN_SMEM_BUDGET = 108 * 1024;   // per CTA (two CTAs share the 227 KB of an SM)
 
-  // the row stays packed (bf16) in registers: 4 registers per chunk keep the occupancy high enough to cover HBM latency
-  uint4 raw[CH];
-  float sum = 0.f;
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// v[r] = this thread's partial of row r  ->  stat[r] = sum over the CTA.  `between` runs after the first barrier (every
+// thread has passed the code before the call).  Hazards: `red` of one statistic is rewritten only after two further
+// barriers; `stat` is rewritten by the one-warp-per-row step of the same statistic in the next unit, which follows that
+// unit's first barrier, which every thread reaches only after its last read of `stat` in this unit.
+template <typename F>
+__device__ __forceinline__ void ln_block_stat(float (&v)[LN_RB], float* red, float* stat, int warp, int lane, int nwarps, F between) {
 #pragma unroll
-  for (int i = 0; i < CH; ++i) {
-    const int c = lane + i * 32;
-    raw[i] = make_uint4(0u, 0u, 0u, 0u);
-    if (c < nchunk) raw[i] = ldg_nc_v4(x + c * 8);
+  for (int r = 0; r < LN_RB; ++r) v[r] = warp_sum(v[r]);
+  if (lane == 0) {
+#pragma unroll
+    for (int r = 0; r < LN_RB; ++r) red[r * LN_MAX_WARPS + warp] = v[r];
   }
-#pragma unroll
-  for (int i = 0; i < CH; ++i) {
-    float v[8];
-    unpack8(raw[i], v);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) sum += v[e];                 // padding chunks are zero
+  __syncthreads();
+  between();
+  for (int r = warp; r < LN_RB; r += nwarps) {
+    float t = lane < nwarps ? red[r * LN_MAX_WARPS + lane] : 0.f;
+    t = warp_sum(t);
+    if (lane == 0) stat[r] = t;
   }
-  const float mean = warp_sum(sum) / (float)p.D;
-  float sq = 0.f;
-#pragma unroll
-  for (int i = 0; i < CH; ++i) {
-    if (lane + i * 32 < nchunk) {
-      float v[8];
-      unpack8(raw[i], v);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float d = v[e] - mean;
-        sq += d * d;
-      }
+  __syncthreads();
+}
+
+template <int WARPS>   // upper bound of the block size: sets the register budget (LN_CTAS CTAs per SM)
+__global__ void __launch_bounds__(WARPS * 32, LN_CTAS) ln_modulate_kernel(const LnModParams p, int units_text, int units_video,
+                                                                          int stages) {
+  extern __shared__ __align__(128) uint8_t ln_smem[];
+  __shared__ float red[2][LN_RB * LN_MAX_WARPS];
+  __shared__ float stat[2][LN_RB];
+  __shared__ uint64_t full[LN_MAX_STAGES];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int col = threadIdx.x * 8;
+  const bool active = col < p.D;
+  const int batch = (int)(p.rows / p.rows_per_batch);
+  const int units_per_batch = units_text + units_video;
+  const int total_units = batch * units_per_batch;
+  const float invD = 1.0f / (float)p.D;
+  const uint32_t row_bytes = (uint32_t)p.D * 2u, stage_bytes = row_bytes * LN_RB;
+
+  // unit u -> (batch, expert, first row, row count)
+  auto unit = [&](int u, int& b, int& text, int& s0, int& n) {
+    b = u / units_per_batch;
+    const int k = u - b * units_per_batch;
+    text = k < units_text ? 1 : 0;
+    s0 = text ? k * LN_RB : p.text_len + (k - units_text) * LN_RB;
+    n = min(LN_RB, (text ? p.text_len : p.rows_per_batch) - s0);
+  };
+  auto fetch = [&](int u, int stage) {                         // one thread: the unit's rows are contiguous in x
+    int b, text, s0, n;
+    unit(u, b, text, s0, n);
+    const __nv_bfloat16* x = p.x + ((long long)b * p.x_batch_rows + p.x_row_offset + s0) * p.D;
+    mbar_arrive_expect_tx(&full[stage], (uint32_t)n * row_bytes);
+    bulk_load(ln_smem + (size_t)stage * stage_bytes, x, (uint32_t)n * row_bytes, &full[stage]);
+  };
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < stages; ++i) mbar_init(&full[i], 1);
+    fence_barrier_init();
+    for (int i = 0; i < stages; ++i) {
+      const long long u = (long long)blockIdx.x + (long long)i * gridDim.x;
+      if (u < total_units) fetch((int)u, i);
     }
   }
-  const float rstd = rsqrtf(warp_sum(sq) / (float)p.D + p.eps);
+  __syncthreads();
 
-  const bool text = s < p.text_len;
-  const float* shift = p.mod ? p.mod + (long long)b * p.mod_batch_stride + (text ? p.shift_text_off : p.shift_video_off) : nullptr;
-  const float* scale = p.mod ? p.mod + (long long)b * p.mod_batch_stride + (text ? p.scale_text_off : p.scale_video_off) : nullptr;
+  float A[8], C[8];
+  int cur_b = -1, cur_text = -1;
+  int stage = 0;
+  uint32_t phase = 0;
+  for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+    int b, text, s0, n;
+    unit(u, b, text, s0, n);
+    if (active && (b != cur_b || text != cur_text)) {           // new (batch, expert): rebuild the coefficient registers
+      cur_b = b; cur_text = text;
+      float g[8], be[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(p.gamma + col)), g);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(p.beta + col)), be);
+      if (p.mod) {
+        const float* sh = p.mod + (long long)b * p.mod_batch_stride + (text ? p.shift_text_off : p.shift_video_off) + col;
+        const float* sc = p.mod + (long long)b * p.mod_batch_stride + (text ? p.scale_text_off : p.scale_video_off) + col;
 #pragma unroll
-  for (int i = 0; i < CH; ++i) {
-    const int c = lane + i * 32;
-    if (c < nchunk) {
-      float v[8], g[8], be[8], o[8];
-      unpack8(raw[i], v);
-      unpack8(__ldg(reinterpret_cast<const uint4*>(p.gamma) + c), g);
-      unpack8(__ldg(reinterpret_cast<const uint4*>(p.beta) + c), be);
+        for (int e = 0; e < 8; ++e) {
+          const float one_plus = 1.f + __ldg(sc + e);
+          A[e] = g[e] * one_plus;
+          C[e] = fmaf(be[e], one_plus, __ldg(sh + e));
+        }
+      } else {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) o[e] = (v[e] - mean) * rstd * g[e] + be[e];
-      if (shift) {
-        const float4 s0 = __ldg(reinterpret_cast<const float4*>(shift + c * 8));
-        const float4 s1 = __ldg(reinterpret_cast<const float4*>(shift + c * 8) + 1);
-        const float4 c0 = __ldg(reinterpret_cast<const float4*>(scale + c * 8));
-        const float4 c1 = __ldg(reinterpret_cast<const float4*>(scale + c * 8) + 1);
-        o[0] = o[0] * (1.f + c0.x) + s0.x; o[1] = o[1] * (1.f + c0.y) + s0.y;
-        o[2] = o[2] * (1.f + c0.z) + s0.z; o[3] = o[3] * (1.f + c0.w) + s0.w;
-        o[4] = o[4] * (1.f + c1.x) + s1.x; o[5] = o[5] * (1.f + c1.y) + s1.y;
-        o[6] = o[6] * (1.f + c1.z) + s1.z; o[7] = o[7] * (1.f + c1.w) + s1.w;
+        for (int e = 0; e < 8; ++e) { A[e] = g[e]; C[e] = be[e]; }
       }
-      *reinterpret_cast<uint4*>(y + c * 8) = pack8(o);
     }
+    __nv_bfloat16* y = p.y + ((long long)b * p.rows_per_batch + s0) * p.D + col;
+
+    mbar_wait(&full[stage], phase);
+    float v[LN_RB][8];                                             // unpacked once; three passes read them
+    float st[LN_RB];
+    const uint8_t* src = ln_smem + (size_t)stage * stage_bytes + (size_t)col * 2;
+#pragma unroll
+    for (int r = 0; r < LN_RB; ++r) {
+      uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+      if (active && r < n) raw = *reinterpret_cast<const uint4*>(src + (size_t)r * row_bytes);
+      unpack8(raw, v[r]);
+      st[r] = ((v[r][0] + v[r][1]) + (v[r][2] + v[r][3])) + ((v[r][4] + v[r][5]) + (v[r][6] + v[r][7]));
+    }
+    // after the first barrier of this reduction every thread holds its part of the stage in registers: refill the stage
+    ln_block_stat(st, red[0], stat[0], warp, lane, nwarps, [&]() {
+      const long long un = (long long)u + (long long)stages * gridDim.x;
+      if (threadIdx.x == 0 && un < total_units) fetch((int)un, stage);
+    });
+#pragma unroll
+    for (int r = 0; r < LN_RB; ++r) {
+      const float mean = stat[0][r] * invD;
+      float q = 0.f;
+      if (active) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { const float d = v[r][e] - mean; q = fmaf(d, d, q); }
+      }
+      st[r] = q;
+    }
+    ln_block_stat(st, red[1], stat[1], warp, lane, nwarps, []() {});
+#pragma unroll
+    for (int r = 0; r < LN_RB; ++r) {
+      if (active && r < n) {
+        const float rstd = rsqrtf(stat[1][r] * invD + p.eps);
+        const float nmr = -stat[0][r] * invD * rstd;
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = fmaf(fmaf(v[r][e], rstd, nmr), A[e], C[e]);
+        *reinterpret_cast<uint4*>(y + (long long)r * p.D) = pack8(o);
+      }
+    }
+    if (++stage == stages) { stage = 0; phase ^= 1; }
   }
 }
 
@@ -325,26 +412,55 @@ int launch_a2a_unpack_heads(const void* src, void* const* dst, int slots, int pe
 int launch_ln_modulate(const LnModParams& p, cudaStream_t st) {
   VP_REQUIRE(p.rows > 0 && p.D > 0 && p.D % 8 == 0, VP_ERR_BAD_SHAPE, "ln_modulate: D must be a positive multiple of 8");
   VP_REQUIRE(p.D <= 4096, VP_ERR_UNSUPPORTED, "ln_modulate: D > 4096 not supported");
-  const int nchunk = p.D / 8;
-  const int ch = (nchunk + 31) / 32;
-  const unsigned grid = (unsigned)((p.rows + 7) / 8);
+  VP_REQUIRE(p.rows_per_batch > 0 && p.rows % p.rows_per_batch == 0, VP_ERR_BAD_SHAPE, "ln_modulate: rows must be batch * rows_per_batch");
   const bool dbl = p.gamma2 != nullptr;
-  if (dbl) VP_REQUIRE(p.mod != nullptr, VP_ERR_BAD_SHAPE, "ln_double: modulation table required");
-#define VP_LN_CASE(N)                                                   \
-  if (ch <= N) {                                                        \
-    if (dbl) ln_double_kernel<N><<<grid, 256, 0, st>>>(p);              \
-    else ln_modulate_kernel<N><<<grid, 256, 0, st>>>(p);                \
-    VP_CHECK_CUDA(cudaGetLastError());                                  \
-    return VP_OK;                                                       \
+  if (dbl) {
+    VP_REQUIRE(p.mod != nullptr, VP_ERR_BAD_SHAPE, "ln_double: modulation table required");
+    const int ch = (p.D / 8 + 31) / 32;
+    const unsigned grid = (unsigned)((p.rows + 7) / 8);
+#define VP_LN_CASE(N)                                      \
+  if (ch <= N) {                                           \
+    ln_double_kernel<N><<<grid, 256, 0, st>>>(p);          \
+    VP_CHECK_CUDA(cudaGetLastError());                     \
+    return VP_OK;                                          \
   }
-  VP_LN_CASE(1)
-  VP_LN_CASE(2)
-  VP_LN_CASE(4)
-  VP_LN_CASE(8)
-  VP_LN_CASE(12)
-  VP_LN_CASE(16)
+    VP_LN_CASE(1)
+    VP_LN_CASE(2)
+    VP_LN_CASE(4)
+    VP_LN_CASE(8)
+    VP_LN_CASE(12)
+    VP_LN_CASE(16)
 #undef VP_LN_CASE
-  return fail(VP_ERR_UNSUPPORTED, "ln_modulate: unsupported width");
+    return fail(VP_ERR_UNSUPPORTED, "ln_double: unsupported width");
+  }
+  LnModParams q = p;
+  if (q.mod == nullptr || q.text_len < 0) q.text_len = 0;
+  if (q.text_len > q.rows_per_batch) q.text_len = q.rows_per_batch;
+  const int threads = ((p.D / 8 + 31) / 32) * 32;
+  const int units_text = (q.text_len + LN_RB - 1) / LN_RB;
+  const int units_video = (q.rows_per_batch - q.text_len + LN_RB - 1) / LN_RB;
+  const long long total = (p.rows / p.rows_per_batch) * (long long)(units_text + units_video);
+  const int sms = sm_count();
+  if (sms <= 0) return fail(VP_ERR_CUDA, "no CUDA device");
+  VP_REQUIRE((reinterpret_cast<uintptr_t>(p.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 15) == 0, VP_ERR_BAD_ALIGN,
+             "ln_modulate: x and y must be 16-byte aligned");
+  long long grid = (long long)sms * LN_CTAS;           // resident CTAs per SM (launch bounds), persistent
+  if (grid > total) grid = total;
+  const int stage_bytes = LN_RB * p.D * 2;
+  int stages = LN_SMEM_BUDGET / stage_bytes;
+  if (stages > LN_MAX_STAGES) stages = LN_MAX_STAGES;
+  if (stages < 1) stages = 1;
+  const size_t smem = (size_t)stages * stage_bytes;
+  static bool configured = false;
+  if (!configured) {
+    VP_CHECK_CUDA(cudaFuncSetAttribute(ln_modulate_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, LN_SMEM_BUDGET));
+    VP_CHECK_CUDA(cudaFuncSetAttribute(ln_modulate_kernel<LN_MAX_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, LN_SMEM_BUDGET));
+    configured = true;
+  }
+  if (threads <= 12 * 32) ln_modulate_kernel<12><<<(unsigned)grid, threads, smem, st>>>(q, units_text, units_video, stages);
+  else ln_modulate_kernel<LN_MAX_WARPS><<<(unsigned)grid, threads, smem, st>>>(q, units_text, units_video, stages);
+  VP_CHECK_CUDA(cudaGetLastError());
+  return VP_OK;
 }
 
 int launch_gemv(const float* in, const void* W, const void* bias, float* out, int B, int N, int K, int act_silu,
