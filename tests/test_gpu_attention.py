@@ -70,3 +70,43 @@ def test_attention_large_scores_rescale_path(ops):
     out = torch.zeros(B, S, H * 64, dtype=BF16, device="cuda")
     ops.attention(q, k, v, out, B, H, S, S, 0.125)
     assert_close_bf16("attention rescale", out, _to_out_layout(_ref(q, k, v)), cos_min=0.9995, rel_max=5e-2)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE.json full size (S = 17 776 tokens, 48 heads x 64, CFG batch 2)
+# ---------------------------------------------------------------------------------------------------------------------
+S_FULL = 17776
+
+
+def test_attention_full_sequence_against_fp32(ops):
+    """Two heads of the production sequence length against explicit fp32 softmax attention (1.3 GB of scores per head)."""
+    B, H = 1, 2
+    q, k, v = _randn(B, H, S_FULL, 64, seed=11), _randn(B, H, S_FULL, 64, seed=12), _randn(B, H, S_FULL, 64, seed=13)
+    out = torch.zeros(B, S_FULL, H * 64, dtype=BF16, device="cuda")
+    ops.attention(q, k, v, out, B, H, S_FULL, S_FULL, 0.125)
+    assert_close_bf16("attention S=17776", out, _to_out_layout(_ref(q, k, v)), cos_min=0.9998, rel_max=3e-2)
+    # doubled K/V of the ID-resample processor (L_kv = 35 552), one head
+    q1, k1, v1 = q[:, :1].contiguous(), k[:, :1].contiguous(), v[:, :1].contiguous()
+    k2, v2 = _randn(1, 1, S_FULL, 64, seed=14), _randn(1, 1, S_FULL, 64, seed=15)
+    out1 = torch.zeros(1, S_FULL, 64, dtype=BF16, device="cuda")
+    ops.attention(q1, k1, v1, out1, 1, 1, S_FULL, S_FULL, 0.125, k1=k2, v1=v2, kv_len1=S_FULL)
+    ref = _ref(q1, torch.cat([k1, k2], dim=2), torch.cat([v1, v2], dim=2))
+    assert_close_bf16("attention S=17776, L_kv=35552", out1, _to_out_layout(ref), cos_min=0.9998, rel_max=3e-2)
+
+
+def test_attention_full_size_properties(ops):
+    """Size-independent properties on the whole production problem (B = 2, 48 heads, S = 17 776):
+    softmax rows sum to one (V = 1 gives exactly 1), and the output is linear in V."""
+    B, H = 2, 48
+    q, k = _randn(B, H, S_FULL, 64, seed=21), _randn(B, H, S_FULL, 64, seed=22)
+    ones = torch.ones(B, H, S_FULL, 64, dtype=BF16, device="cuda")
+    out = torch.zeros(B, S_FULL, H * 64, dtype=BF16, device="cuda")
+    ops.attention(q, k, ones, out, B, H, S_FULL, S_FULL, 0.125)
+    assert (out.float() - 1.0).abs().max().item() <= 2 ** -7, "softmax rows do not sum to one"
+    v1, v2 = _randn(B, H, S_FULL, 64, seed=23), _randn(B, H, S_FULL, 64, seed=24)
+    o1, o2, o12 = (torch.zeros_like(out) for _ in range(3))
+    ops.attention(q, k, v1, o1, B, H, S_FULL, S_FULL, 0.125)
+    ops.attention(q, k, v2, o2, B, H, S_FULL, S_FULL, 0.125)
+    ops.attention(q, k, (v1.float() + 2.0 * v2.float()).to(BF16), o12, B, H, S_FULL, S_FULL, 0.125)
+    lin = o1.float() + 2.0 * o2.float()
+    assert_close_bf16("attention linearity in V (full size)", o12, lin, cos_min=0.9995, rel_max=5e-2)

@@ -130,3 +130,26 @@ def test_install_patch_is_absent_on_gpu_box_or_works():
     if not has:
         with pytest.raises(Exception):
             vp.install()
+
+
+def test_full_size_single_layer_against_oracle():
+    """BASELINE.json config 2 shapes exactly (49x480x720 -> 17 776 tokens, D = 3072, 48 heads, CFG batch 2), one backbone
+    layer + one branch layer (the 42-layer stack repeats this layer; 2 + 1 layers at this width are covered above)."""
+    from oracle import cogvideox_oracle as O
+    cfg = O.full_config(num_layers=1)
+    cfg_b = O.full_config(num_layers=1)
+    sd_t = O.init_state_dict(cfg, 43, device="cuda")
+    sd_b = O.init_state_dict(cfg_b, 44, branch=True, device="cuda")
+    tr, br = _models(cfg, cfg_b, sd_t, sd_b)
+    inp = O.make_inputs(cfg, 5, device="cuda", rect_mask=True)
+    samples, out, hs, rmask = _run_ours(tr, br, inp)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    r32 = lambda sd: {k: v.to(BF16).float() for k, v in sd.items()}   # noqa: E731
+    with torch.no_grad():
+        rs, (rout, rhs, rrm) = O.denoise_step(r32(sd_t), r32(sd_b), cfg, cfg_b, inp, head_chunk=2)
+    assert out.shape == (2, 13, 16, 60, 90) and hs[-1].shape == (2, 17776, 3072)
+    assert torch.equal(rmask, rrm)
+    assert_close_bf16("full-size.branch[0]", samples[0], rs[0], COS_MIN, REL_MAX)
+    assert_close_bf16("full-size.hs_last", hs[-1], rhs[-1], COS_MIN, REL_MAX)
+    assert_close_bf16("full-size.noise_pred", out, rout, COS_MIN, REL_MAX)
