@@ -156,6 +156,13 @@ def main() -> None:
         run_reference(args)
         return
 
+    # rank 0 prints exactly ONE line on stdout: libraries that write to fd 1 (NCCL's version banner) go to stderr instead
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line: str) -> None:
+        os.write(real_stdout, (line + "\n").encode())
+
     import torch
     import torch.distributed as dist
     import videopainter_b200 as vp
@@ -285,7 +292,9 @@ def main() -> None:
            "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
            "config": {"workload": "CogVideoX-5B-I2V (42 layers, 48x64 heads) + 2-layer VideoPainter branch, one denoise step at "
                                   "49x480x720 (17776 tokens), CFG batch 2, return_hidden_states=True as PIPE:967-980",
-                      "parallelism": plan.describe(), "l2": "per-step working set (11.7 GB weights, 218 MB activations per "
+                      "parallelism": plan.describe() + ((", all-to-all fused into the GEMM / attention epilogues over NVLink peer memory"
+                                                         if parallel.current().p2p else ", NCCL all-to-all") if plan.sp > 1 else ""),
+                      "l2": "per-step working set (11.7 GB weights, 218 MB activations per "
                       "layer) exceeds the 126 MB L2; no explicit flush", "random_init": True},
            "step_tflops": flops / (ms_per_step * 1e-3) / 1e12,
            "frac_of_bf16_peak": {"sustained": flops / (ms_per_step * 1e-3) / 1e12 / (peak_tf * world),
@@ -301,7 +310,7 @@ def main() -> None:
     if args.breakdown:
         with open(args.breakdown, "w") as f:
             json.dump({"ms_per_step": ms_per_step, "kernels": breakdown, "clocks": clocks}, f, indent=1)
-    print(json.dumps(out))
+    emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 

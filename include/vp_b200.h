@@ -100,7 +100,25 @@ int vp_gemm_qkv(const void* a, long long lda, const void* w, long long ldw, cons
                 const void* norm_k_w, const void* norm_k_b, float qk_eps, const float* rope_cos, const float* rope_sin,
                 int text_len, int heads_per_dest, long long dest_stride, void* stream);
 
-/* Ulysses receive side: src [peers][slots][heads_local][rows_per_peer][64] (what the all-to-all delivers when every peer
+/* ---- Ulysses over NVLink peer memory: the all-to-all is fused into the producing kernels' epilogues ------------------
+ * Every rank of the sequence-parallel group owns a q/k/v buffer [slot][heads/peers][seq_total][64] and an attention-output
+ * buffer [peers][seq_total/peers][ldo]; `peer_*` are HOST arrays of DEVICE pointers to all ranks' buffers (own rank included,
+ * peer memory mapped through CUDA IPC), indexed by rank.  vp_gemm_qkv_peer writes head h of its rows straight into rank
+ * h / (heads/peers)'s buffer at token rows [row_offset, row_offset + m) (q_out .. v2_out select the slot: they point into
+ * the LOCAL buffer local_base); vp_attention_peer stores query row r into rank r / (seq_q/peers)'s output buffer at source
+ * slot my_rank.  vp_peer_barrier orders the two: all earlier peer stores of every rank are visible to every rank after it
+ * (system-scope release / acquire on per-rank flag words; epoch must increase by one per call, identically on all ranks). */
+int vp_gemm_qkv_peer(const void* a, long long lda, const void* w, long long ldw, const void* bias, int m, int k, int heads,
+                     int qkv_first, void* q_out, void* k_out, void* v_out, void* k2_out, void* v2_out, const uint8_t* mask2,
+                     const float* row_scale, const void* norm_q_w, const void* norm_q_b, const void* norm_k_w,
+                     const void* norm_k_b, float qk_eps, const float* rope_cos, const float* rope_sin, int text_len,
+                     void* const* peer_base, int peers, const void* local_base, int seq_total, int row_offset, void* stream);
+int vp_attention_peer(const void* q, const void* k0, const void* v0, int kv_len0, const void* k1, const void* v1, int kv_len1,
+                      void* const* peer_out, int peers, int my_rank, int ldo, int heads, int seq_q, float softmax_scale,
+                      float out_scale, void* stream);
+int vp_peer_barrier(void* const* peer_flags, int peers, int my_rank, unsigned int epoch, void* stream);
+
+/* Ulysses receive side (NCCL path): src [peers][slots][heads_local][rows_per_peer][64] (what the all-to-all delivers when every peer
  * sent its vp_gemm_qkv destination block) -> dst[slot] [heads_local][peers * rows_per_peer][64], the layout vp_attention
  * reads.  slots <= 5 (q, k, v, k2, v2); dst pointers beyond `slots` are ignored. */
 int vp_a2a_unpack_heads(const void* src, void* dst0, void* dst1, void* dst2, void* dst3, void* dst4, int slots, int peers,

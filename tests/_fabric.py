@@ -17,9 +17,30 @@ class Fabric:
 
 
 class ThreadRuntime(parallel.Runtime):
-    def __init__(self, plan: parallel.Plan, fabric: Fabric):
-        super().__init__(plan)
+    def __init__(self, plan: parallel.Plan, fabric: Fabric, p2p: bool = True):
+        super().__init__(plan, p2p=p2p)
         self.fabric = fabric
+        self._n_share = 0
+
+    # peer memory: the virtual ranks live in one process on one device, so a "peer pointer" is a plain device pointer
+    def share(self, t):
+        f, pl = self.fabric, self.plan
+        key = ("share", self._n_share)
+        self._n_share += 1
+        f.box[(key, pl.rank)] = t
+        f.barrier.wait()
+        ptrs = [f.box[(key, r)].data_ptr() for r in pl.sp_ranks()]
+        f.barrier.wait()
+        return ptrs
+
+    def ready(self):
+        self._sync()
+        self.fabric.barrier.wait()
+
+    def peer_barrier(self, flag_ptrs, epoch):
+        # kernels of different virtual ranks share one GPU: they must not spin on each other, so the barrier is host-side
+        self._sync()
+        self.fabric.barrier.wait()
 
     def _sync(self):
         if torch.cuda.is_available():
@@ -48,14 +69,14 @@ class ThreadRuntime(parallel.Runtime):
         f.barrier.wait()
 
 
-def run_virtual_ranks(world: int, fn):
+def run_virtual_ranks(world: int, fn, p2p: bool = True):
     """fn(rank, runtime) on `world` threads; returns the list of results, re-raises the first failure."""
     fab = Fabric(world)
     res, err = [None] * world, [None] * world
 
     def body(r):
         try:
-            rt = ThreadRuntime(parallel.make_plan(world, r), fab)
+            rt = ThreadRuntime(parallel.make_plan(world, r), fab, p2p=p2p)
             parallel.install(rt)
             if torch.cuda.is_available():
                 torch.cuda.set_device(0)

@@ -35,8 +35,9 @@ def _step(tr, br, inp, attention_kwargs=None):
     return samples, out, hs, rmask
 
 
+@pytest.mark.parametrize("p2p", [True, False], ids=["peer-memory", "nccl-layout"])
 @pytest.mark.parametrize("world,heads,resample", [(2, 2, False), (4, 2, False), (4, 2, True), (8, 4, False)])
-def test_virtual_ranks_match_single_gpu(world, heads, resample):
+def test_virtual_ranks_match_single_gpu(world, heads, resample, p2p):
     from oracle import cogvideox_oracle as O
     cfg = O.tiny_config(num_attention_heads=heads, id_pool_resample_learnable=resample)
     cfg_b = O.tiny_config(num_attention_heads=heads, num_layers=1)
@@ -55,7 +56,7 @@ def test_virtual_ranks_match_single_gpu(world, heads, resample):
         _, outb, _, _ = _step(trr, brr, inp2, attention_kwargs=kw)   # second window: sharded prev states stay on the rank
         return s, out, hs, rm, outb
 
-    res = run_virtual_ranks(world, rank_fn)
+    res = run_virtual_ranks(world, rank_fn, p2p=p2p)
     sp = world // 2
     for r, (s, out, hs, rm, outb) in enumerate(res):
         assert torch.equal(rm, rm1)

@@ -384,6 +384,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       const float inv = p.out_scale / total;
       const int b = bh / p.heads, h = bh - b * p.heads;
       __nv_bfloat16* dst = p.out + ((long long)b * p.seq_q + q_row) * p.ldo + h * DH + half * 32;
+      if (p.peer_out[0]) {                                       // P2P store into the rank that owns this token row
+        const int dest = q_row / p.peer_rows;
+        dst = p.peer_out[dest] + ((long long)p.peer_src * p.peer_rows + (q_row - dest * p.peer_rows)) * p.ldo + h * DH + half * 32;
+      }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         float f[8];
@@ -516,6 +520,8 @@ int launch_attention(const void* q, const void* k0, const void* v0, const void* 
              "attention: bad shape");
   VP_REQUIRE(p.ldo % 8 == 0, VP_ERR_BAD_ALIGN, "attention: output leading dim must be a multiple of 8");
   VP_REQUIRE(p.kv_len1 == 0 || (k1 && v1), VP_ERR_BAD_SHAPE, "attention: second K/V segment missing");
+  VP_REQUIRE(p.peer_out[0] == nullptr || (p.batch == 1 && p.peer_rows > 0 && !p.accumulate), VP_ERR_UNSUPPORTED,
+             "attention: peer output needs batch 1 and no accumulation");
   static bool configured = false;
   if (!configured) {
     VP_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));

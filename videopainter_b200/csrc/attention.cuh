@@ -15,6 +15,11 @@ struct AttnParams {
   int ldo;
   float out_scale;           // out = (accumulate ? out : 0) + out_scale * softmax(QKᵀ)V   (prev-window blend AP:2176-2189)
   int accumulate;
+  // peer mode (Ulysses over NVLink peer memory): when peer_out[0] != null, query row q belongs to rank q / peer_rows and is
+  // stored into that rank's buffer [source rank][peer_rows][ldo] at source slot peer_src; `out` is ignored
+  __nv_bfloat16* peer_out[8];
+  int peer_rows;
+  int peer_src;
 };
 
 int launch_attention(const void* q, const void* k0, const void* v0, const void* k1, const void* v1, const AttnParams& p,

@@ -123,11 +123,18 @@ int vp_gemm_gate_residual(const void* a, long long lda, const void* w, long long
   return launch_gemm(EPI_RESID, a, lda, w, ldw, p, (cudaStream_t)stream);
 }
 
-int vp_gemm_qkv(const void* a, long long lda, const void* w, long long ldw, const void* bias, int m, int k, int batch_rows,
-                int heads, int qkv_first, void* q_out, void* k_out, void* v_out, void* k2_out, void* v2_out,
-                const uint8_t* mask2, const float* row_scale, const void* norm_q_w, const void* norm_q_b,
-                const void* norm_k_w, const void* norm_k_b, float qk_eps, const float* rope_cos, const float* rope_sin,
-                int text_len, int heads_per_dest, long long dest_stride, void* stream) {
+struct PeerDest {
+  void* const* base = nullptr;    // host array of device pointers, one per destination rank
+  int peers = 0;
+  const void* local_base = nullptr;
+  int seq = 0, row_off = 0;
+};
+
+static int gemm_qkv_impl(const void* a, long long lda, const void* w, long long ldw, const void* bias, int m, int k, int batch_rows,
+                         int heads, int qkv_first, void* q_out, void* k_out, void* v_out, void* k2_out, void* v2_out,
+                         const uint8_t* mask2, const float* row_scale, const void* norm_q_w, const void* norm_q_b,
+                         const void* norm_k_w, const void* norm_k_b, float qk_eps, const float* rope_cos, const float* rope_sin,
+                         int text_len, int heads_per_dest, long long dest_stride, const PeerDest& peer, void* stream) {
   VP_REQUIRE(a && w && bias && k_out && v_out && norm_k_w && norm_k_b, VP_ERR_BAD_SHAPE, "gemm_qkv: null pointer");
   VP_REQUIRE(heads_per_dest > 0 && heads % heads_per_dest == 0 && dest_stride % 8 == 0, VP_ERR_BAD_SHAPE,
              "gemm_qkv: heads_per_dest must divide heads");
@@ -150,7 +157,39 @@ int vp_gemm_qkv(const void* a, long long lda, const void* w, long long ldw, cons
   p.rope_cos = rope_cos; p.rope_sin = rope_sin;
   p.text_len = text_len;
   p.heads_per_dest = heads_per_dest; p.dest_stride = dest_stride;
+  if (peer.base) {
+    VP_REQUIRE(peer.peers >= 1 && peer.peers <= 8 && peer.peers * heads_per_dest == heads && peer.local_base && peer.seq > 0 &&
+                   m == batch_rows, VP_ERR_BAD_SHAPE, "gemm_qkv_peer: one sample per rank, peers * heads_per_dest == heads");
+    for (int i = 0; i < peer.peers; ++i) {
+      VP_REQUIRE(peer.base[i] != nullptr, VP_ERR_BAD_SHAPE, "gemm_qkv_peer: null peer pointer");
+      p.peer_base[i] = (__nv_bfloat16*)peer.base[i];
+    }
+    p.local_base = (const __nv_bfloat16*)peer.local_base;
+    p.peer_seq = peer.seq; p.peer_row_off = peer.row_off;
+  }
   return launch_gemm(EPI_QKV, a, lda, w, ldw, p, (cudaStream_t)stream);
+}
+
+int vp_gemm_qkv(const void* a, long long lda, const void* w, long long ldw, const void* bias, int m, int k, int batch_rows,
+                int heads, int qkv_first, void* q_out, void* k_out, void* v_out, void* k2_out, void* v2_out,
+                const uint8_t* mask2, const float* row_scale, const void* norm_q_w, const void* norm_q_b,
+                const void* norm_k_w, const void* norm_k_b, float qk_eps, const float* rope_cos, const float* rope_sin,
+                int text_len, int heads_per_dest, long long dest_stride, void* stream) {
+  return gemm_qkv_impl(a, lda, w, ldw, bias, m, k, batch_rows, heads, qkv_first, q_out, k_out, v_out, k2_out, v2_out, mask2,
+                       row_scale, norm_q_w, norm_q_b, norm_k_w, norm_k_b, qk_eps, rope_cos, rope_sin, text_len, heads_per_dest,
+                       dest_stride, PeerDest{}, stream);
+}
+
+int vp_gemm_qkv_peer(const void* a, long long lda, const void* w, long long ldw, const void* bias, int m, int k, int heads,
+                     int qkv_first, void* q_out, void* k_out, void* v_out, void* k2_out, void* v2_out, const uint8_t* mask2,
+                     const float* row_scale, const void* norm_q_w, const void* norm_q_b, const void* norm_k_w,
+                     const void* norm_k_b, float qk_eps, const float* rope_cos, const float* rope_sin, int text_len,
+                     void* const* peer_base, int peers, const void* local_base, int seq_total, int row_offset, void* stream) {
+  VP_REQUIRE(peer_base && peers >= 1 && heads % peers == 0, VP_ERR_BAD_SHAPE, "gemm_qkv_peer: peers must divide heads");
+  PeerDest pd;
+  pd.base = peer_base; pd.peers = peers; pd.local_base = local_base; pd.seq = seq_total; pd.row_off = row_offset;
+  return gemm_qkv_impl(a, lda, w, ldw, bias, m, k, m, heads, qkv_first, q_out, k_out, v_out, k2_out, v2_out, mask2, row_scale,
+                       norm_q_w, norm_q_b, norm_k_w, norm_k_b, qk_eps, rope_cos, rope_sin, text_len, heads / peers, 0, pd, stream);
 }
 
 int vp_attention(const void* q, const void* k0, const void* v0, int kv_len0, const void* k1, const void* v1, int kv_len1,
@@ -164,6 +203,36 @@ int vp_attention(const void* q, const void* k0, const void* v0, int kv_len0, con
   p.out = (__nv_bfloat16*)out; p.ldo = ldo;
   p.out_scale = out_scale; p.accumulate = accumulate;
   return launch_attention(q, k0, v0, k1, v1, p, (cudaStream_t)stream);
+}
+
+int vp_attention_peer(const void* q, const void* k0, const void* v0, int kv_len0, const void* k1, const void* v1, int kv_len1,
+                      void* const* peer_out, int peers, int my_rank, int ldo, int heads, int seq_q, float softmax_scale,
+                      float out_scale, void* stream) {
+  VP_REQUIRE(q && k0 && v0 && peer_out, VP_ERR_BAD_SHAPE, "attention_peer: null pointer");
+  VP_REQUIRE(peers >= 1 && peers <= 8 && seq_q % peers == 0 && my_rank >= 0 && my_rank < peers, VP_ERR_BAD_SHAPE,
+             "attention_peer: the query rows must divide over 1..8 peers");
+  AttnParams p{};
+  p.batch = 1; p.heads = heads; p.seq_q = seq_q;
+  p.kv_len0 = kv_len0; p.kv_len1 = kv_len1;
+  p.scale_log2 = softmax_scale * 1.4426950408889634f;
+  p.out = (__nv_bfloat16*)peer_out[my_rank]; p.ldo = ldo;
+  p.out_scale = out_scale; p.accumulate = 0;
+  for (int i = 0; i < peers; ++i) {
+    VP_REQUIRE(peer_out[i] != nullptr, VP_ERR_BAD_SHAPE, "attention_peer: null peer pointer");
+    p.peer_out[i] = (__nv_bfloat16*)peer_out[i];
+  }
+  p.peer_rows = seq_q / peers; p.peer_src = my_rank;
+  return launch_attention(q, k0, v0, k1, v1, p, (cudaStream_t)stream);
+}
+
+int vp_peer_barrier(void* const* peer_flags, int peers, int my_rank, unsigned int epoch, void* stream) {
+  VP_REQUIRE(peer_flags && peers >= 1 && peers <= 8 && my_rank >= 0 && my_rank < peers, VP_ERR_BAD_SHAPE, "peer_barrier: bad arguments");
+  uint32_t* f[8];
+  for (int i = 0; i < peers; ++i) {
+    VP_REQUIRE(peer_flags[i] != nullptr, VP_ERR_BAD_SHAPE, "peer_barrier: null flag pointer");
+    f[i] = (uint32_t*)peer_flags[i];
+  }
+  return launch_peer_barrier(f, peers, my_rank, epoch, (cudaStream_t)stream);
 }
 
 int vp_a2a_unpack_heads(const void* src, void* dst0, void* dst1, void* dst2, void* dst3, void* dst4, int slots, int peers,

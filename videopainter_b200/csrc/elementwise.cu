@@ -395,7 +395,40 @@ __global__ void __launch_bounds__(256) a2a_unpack_heads_kernel(const uint4* __re
   }
 }
 
+// Cross-GPU barrier over peer memory: every rank runs one of these on its own GPU.  Thread i tells rank i "rank my_rank has
+// reached epoch" (release store into rank i's flag array, after a system-scope fence that orders this GPU's earlier peer
+// stores), then waits until rank i has said the same to us.  Bounded: a lost peer traps after ~4 s instead of hanging.
+struct PeerFlags { uint32_t* p[8]; };
+__global__ void peer_barrier_kernel(PeerFlags flags, int peers, int my_rank, uint32_t epoch) {
+  const int i = threadIdx.x;
+  if (i >= peers) return;
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(flags.p[i] + my_rank), "r"(epoch) : "memory");
+  const uint32_t* mine = flags.p[my_rank] + i;
+  uint64_t t0 = 0;
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(mine) : "memory");
+    if ((int32_t)(v - epoch) >= 0) break;
+    if ((++spins & 0xfff) == 0) {
+      const uint64_t now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) __trap();
+    }
+  }
+  __threadfence_system();
+}
+
 }  // namespace
+
+int launch_peer_barrier(uint32_t* const* peer_flags, int peers, int my_rank, uint32_t epoch, cudaStream_t st) {
+  PeerFlags f{};
+  for (int i = 0; i < peers; ++i) f.p[i] = peer_flags[i];
+  peer_barrier_kernel<<<1, 32, 0, st>>>(f, peers, my_rank, epoch);
+  VP_CHECK_CUDA(cudaGetLastError());
+  return VP_OK;
+}
 
 int launch_a2a_unpack_heads(const void* src, void* const* dst, int slots, int peers, int heads_local, int rows_per_peer,
                             cudaStream_t st) {

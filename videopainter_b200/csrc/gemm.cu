@@ -146,7 +146,10 @@ __device__ __forceinline__ void epilogue_qkv_head(const GemmParams& p, const uin
   const int head = (n0 % p.d_model) >> 6;
   const float rs = p.row_scale ? p.row_scale[m] : 1.0f;
   const int dest = head / p.heads_per_dest, hl = head - dest * p.heads_per_dest;
-  const long long off = dest * p.dest_stride + (((long long)b * p.heads_per_dest + hl) * p.rows_per_batch + s) * 64;
+  long long off = dest * p.dest_stride + (((long long)b * p.heads_per_dest + hl) * p.rows_per_batch + s) * 64;
+  if (p.peer_base[0]) {           // store into the destination rank's memory (P2P): offset relative to the local twin buffer
+    off = (p.peer_base[dest] - p.local_base) + ((long long)hl * p.peer_seq + p.peer_row_off + s) * 64;
+  }
   if (which == 2) {
     float y[32];
 #pragma unroll

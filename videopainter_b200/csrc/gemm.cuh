@@ -50,6 +50,14 @@ struct GemmParams {
   // heads_per_dest = heads gives the plain [B, H, S, 64]; smaller values lay the heads out per Ulysses destination rank
   int heads_per_dest;
   long long dest_stride;          // elements
+  // peer mode (Ulysses over NVLink peer memory): when peer_base[0] != null the outputs of head h go straight into the
+  // attention layout [slot][heads_per_dest][peer_seq][64] of destination rank h / heads_per_dest, at token row
+  // peer_row_off + s:  dst = peer_base[dest] + (x_out - local_base) + ((h % heads_per_dest) * peer_seq + peer_row_off + s) * 64
+  // (x_out then only selects the slot inside the local copy of that buffer); dest_stride is ignored
+  __nv_bfloat16* peer_base[8];
+  const __nv_bfloat16* local_base;
+  int peer_seq;
+  int peer_row_off;
   __nv_bfloat16* q_out;           // [B, H, S, 64]
   __nv_bfloat16* k_out;
   __nv_bfloat16* v_out;

@@ -151,18 +151,24 @@ class _Workspace:
     """Scratch buffers of one (batch, shard) shape.  B = samples this rank runs, R = token rows it owns (R = S unless the
     sequence is sharded), Hl = heads it attends (Hl = H unless sharded)."""
 
-    def __init__(self, pm: PackedModel, B: int, S: int, Sv: int, sh: Shard, device):
+    def __init__(self, pm: PackedModel, B: int, S: int, Sv: int, sh: Shard, device, rt=None):
         D, H = pm.dims.D, pm.dims.heads
         R, Hl, P = sh.rows, sh.heads_local, sh.sp
         if P > 1 and B != 1:
             raise ValueError("sequence parallelism runs one sample per rank (the CFG halves live on disjoint groups)")
         e = lambda *shape, dtype=BF16: torch.empty(*shape, dtype=dtype, device=device)   # noqa: E731
         self.xn = e(B * R, D)
-        self.q = e(B, Hl, S, 64)
-        self.k = e(B, Hl, S, 64)
-        self.v = e(B, Hl, S, 64)
-        self.k2 = None
-        self.v2 = None
+        # peer mode: q, k, v, k2, v2 are the five slots of one buffer that the peers' QKV epilogues write into
+        self.peer = rt is not None and rt.p2p and P > 1
+        if self.peer:
+            self.qkv_sym = e(5, Hl, S, 64)
+            self.q, self.k, self.v, self.k2, self.v2 = (self.qkv_sym[i].unsqueeze(0) for i in range(5))
+        else:
+            self.q = e(B, Hl, S, 64)
+            self.k = e(B, Hl, S, 64)
+            self.v = e(B, Hl, S, 64)
+            self.k2 = None
+            self.v2 = None
         self.ao = e(B * S, Hl * 64)                     # attention output, token-major (send buffer of all-to-all #2)
         self.xmid = e(B, R, D)
         self.ffm = e(B * R, 4 * D)
@@ -178,6 +184,20 @@ class _Workspace:
         self._recv = {}
         self.ao_recv = e(P, R, Hl * 64) if P > 1 else None
         self.xfull = None
+        if self.peer:
+            self.rt = rt
+            self.flags = torch.zeros(16, dtype=torch.int32, device=device)
+            self.epoch = 0
+            self.ptrs_qkv = rt.share(self.qkv_sym)
+            self.ptrs_ao = rt.share(self.ao_recv)
+            self.ptrs_flags = rt.share(self.flags)
+            rt.ready()
+
+    def peer_sync(self):
+        """All peer stores issued so far by every rank of the group are visible to every rank after this point of the
+        stream."""
+        self.epoch += 1
+        self.rt.peer_barrier(self.ptrs_flags, self.epoch)
 
     def second_kv(self):
         if self.k2 is None:
@@ -195,12 +215,12 @@ class _Workspace:
         return self._send[slots], self._recv[slots]
 
 
-def _workspace(pm: PackedModel, B, S, Sv, sh: Shard, device) -> _Workspace:
-    key = (B, S, Sv, sh.sp, sh.sp_rank, str(device))
+def _workspace(pm: PackedModel, B, S, Sv, sh: Shard, device, rt=None) -> _Workspace:
+    key = (B, S, Sv, sh.sp, sh.sp_rank, str(device), id(rt))
     ws = pm.workspace.get(key)
     if ws is None:
         pm.workspace.clear()
-        ws = _Workspace(pm, B, S, Sv, sh, device)
+        ws = _Workspace(pm, B, S, Sv, sh, device, rt)
         pm.workspace[key] = ws
     return ws
 
@@ -276,6 +296,13 @@ def _qkv(pm, blk, ws, xn, which_first, rope, mask2=None, row_scale=None, masked_
         ops.gemm_qkv(xn, w, b, M, D, R, H, which_first, q_o, k_o, v_o, nq, nk, 1e-6, rope_l, text_l, k2_out=k2_o, v2_out=v2_o,
                      mask2=mask2, row_scale=row_scale)
         return
+    if ws.peer:                                                  # epilogue stores straight into the owners' buffers
+        q_o = outs[0] if which_first == 0 else None
+        k_o, v_o = (outs[1], outs[2]) if which_first == 0 else (outs[0], outs[1])
+        k2_o, v2_o = (outs[3], outs[4]) if masked_copy else (None, None)
+        ops.gemm_qkv_peer(xn, w, b, M, D, H, which_first, q_o, k_o, v_o, nq, nk, 1e-6, rope_l, text_l, ws.ptrs_qkv, ws.qkv_sym,
+                          S, sh.row0, k2_out=k2_o, v2_out=v2_o, mask2=mask2, row_scale=row_scale)
+        return
     slots = len(outs)
     send, recv = ws.exchange(slots)
     sl = [send[0, i] for i in range(slots)]                      # destination 0's blocks; the kernel adds dest * dest_stride
@@ -303,10 +330,21 @@ def _block(pm: PackedModel, blk: PackedBlock, ws: _Workspace, x_in: torch.Tensor
     use_prev = prev is not None and prev_w is not None and prev_w > 0.0
     scale = 1.0 / math.sqrt(d.head_dim)
     ldo = Hl * 64
+    peer = ws.peer
+
+    def attend(k1=None, v1=None, kv_len1=0):
+        if peer:
+            ws.peer_sync()                                            # every rank's q / k / v rows have landed
+            ops.attention_peer(ws.q, ws.k, ws.v, ws.ptrs_ao, sh.sp_rank, ldo, Hl, S, S, scale, k1=k1, v1=v1, kv_len1=kv_len1)
+            ws.peer_sync()                                            # every rank's output rows have landed in ao_recv
+        else:
+            ops.attention(ws.q, ws.k, ws.v, ws.ao, B, Hl, S, S, scale, k1=k1, v1=v1, kv_len1=kv_len1, ldo=ldo)
+
+    o_exchanged = peer
     if d.resample and not use_prev:                                   # AP:2255-2256: masked copy of own K/V
         _qkv(pm, blk, ws, ws.xn, 0, rope, mask2=resample_mask_u8, masked_copy=True, group=group)
         k2, v2 = ws.second_kv()
-        ops.attention(ws.q, ws.k, ws.v, ws.ao, B, Hl, S, S, scale, k1=k2, v1=v2, kv_len1=S, ldo=ldo)
+        attend(k2, v2, S)
     else:
         _qkv(pm, blk, ws, ws.xn, 0, rope, group=group)
         if use_prev:
@@ -315,18 +353,24 @@ def _block(pm: PackedModel, blk: PackedBlock, ws: _Workspace, x_in: torch.Tensor
             k2, v2 = ws.second_kv()
             if d.resample:                                            # AP:2247-2252, one softmax over 2S keys
                 _qkv(pm, blk, ws, ws.xn, 1, rope, row_scale=prev_mask, group=group)
-                ops.attention(ws.q, ws.k, ws.v, ws.ao, B, Hl, S, S, scale, k1=k2, v1=v2, kv_len1=S, ldo=ldo)
+                attend(k2, v2, S)
             else:                                                     # AP:2156-2189, blend of two attentions
                 _qkv(pm, blk, ws, ws.xn, 1, rope, group=group)
+                if peer:
+                    ws.peer_sync()
                 ops.attention(ws.q, ws.k, ws.v, ws.ao, B, Hl, S, S, scale, out_scale=1.0 - prev_w, ldo=ldo)
                 ops.attention(ws.q, k2, v2, ws.ao, B, Hl, S, S, scale, out_scale=prev_w, accumulate=True, ldo=ldo)
+                o_exchanged = False                                   # accumulated locally: exchanged through NCCL below
         else:
-            ops.attention(ws.q, ws.k, ws.v, ws.ao, B, Hl, S, S, scale, ldo=ldo)
+            attend()
     # to_out + gated residual (AP:2202, T3D:169-170): gate = chunk 2 (video) / 5 (text)
     a_kw = {}
     ao = ws.ao
     if sh.sp > 1:                                                      # heads gathered from the peers: [peer][row][Hl * 64]
-        group.all_to_all(ws.ao_recv, ws.ao)
+        if not o_exchanged:
+            group.all_to_all(ws.ao_recv, ws.ao)
+            if peer:
+                ws.peer_sync()                                        # ao_recv is peer-written in the next block: keep order
         ao = ws.ao_recv
         a_kw = dict(lda=ldo, a_k_chunk=ldo, a_chunk_stride=R * ldo)
     ops.gemm_gate_residual(ao, blk.out_w, blk.out_b, ws.xmid, M, D, D, rows_per_batch=R, out_batch_rows=R, out_row_offset=0,
@@ -401,7 +445,7 @@ def branch_forward(pm: PackedModel, hidden_states: torch.Tensor, encoder_hidden_
     group = rt                                                        # collectives of this rank (None on one GPU)
     if torch.is_tensor(timestep) and timestep.ndim > 0 and timestep.shape[0] == Bg:
         timestep = timestep[bs]
-    ws = _workspace(pm, B, S, Sv, sh, dev)
+    ws = _workspace(pm, B, S, Sv, sh, dev, rt)
     emb = _time_embedding(pm, timestep, B, dev)
     rope = _prep_rope(image_rotary_emb, dev, Sv, sh)
     R = sh.rows
@@ -450,7 +494,7 @@ def transformer_forward(pm: PackedModel, hidden_states: torch.Tensor, encoder_hi
     R, St_l, Sv_l = sh.rows, sh.text_rows, sh.video_rows
     if torch.is_tensor(timestep) and timestep.ndim > 0 and timestep.shape[0] == Bg:
         timestep = timestep[bs]
-    ws = _workspace(pm, B, S, Sv, sh, dev)
+    ws = _workspace(pm, B, S, Sv, sh, dev, rt)
     emb = _time_embedding(pm, timestep, B, dev)
     rope = _prep_rope(image_rotary_emb, dev, Sv, sh)
 

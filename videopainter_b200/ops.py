@@ -169,6 +169,39 @@ def gemm_qkv(a, w, bias, m, k, batch_rows, heads, qkv_first, q_out, k_out, v_out
         _stream()), "vp_gemm_qkv")
 
 
+def _ptr_array(ptrs):
+    import ctypes as C
+    return (C.c_void_p * len(ptrs))(*ptrs)
+
+
+@_timed('gemm_qkv', lambda a, w, bias, m, k, heads, qkv_first, *r, **kw: 2.0 * m * k * (3 - qkv_first) * heads * 64)
+def gemm_qkv_peer(a, w, bias, m, k, heads, qkv_first, q_out, k_out, v_out, norm_q, norm_k, qk_eps, rope, text_len, peer_ptrs,
+                  local_base, seq_total, row_offset, k2_out=None, v2_out=None, mask2=None, row_scale=None, ldw=None):
+    """QKV GEMM whose epilogue stores each head into its destination rank's attention buffer over peer memory
+    (include/vp_b200.h vp_gemm_qkv_peer).  peer_ptrs: data pointers of every rank's buffer, by rank."""
+    cos, sin = (None, None) if rope is None else rope
+    check(lib().vp_gemm_qkv_peer(
+        _p(a, BF16, "qkv.a"), k, _p(w, BF16, "qkv.w") if w.is_contiguous() else w.data_ptr(), ldw or k, _p(bias, BF16, "qkv.bias"),
+        m, k, heads, qkv_first, _base(q_out), _base(k_out), _base(v_out), _base(k2_out), _base(v2_out),
+        _p(mask2, torch.uint8, "qkv.mask2"), _p(row_scale, torch.float32, "qkv.row_scale"),
+        _p(norm_q[0], BF16) if norm_q else None, _p(norm_q[1], BF16) if norm_q else None, _p(norm_k[0], BF16), _p(norm_k[1], BF16),
+        float(qk_eps), _base(cos, torch.float32), _base(sin, torch.float32), text_len, _ptr_array(peer_ptrs), len(peer_ptrs),
+        _base(local_base), seq_total, row_offset, _stream()), "vp_gemm_qkv_peer")
+
+
+@_timed('attention', lambda q, k0, v0, peer_ptrs, my_rank, ldo, heads, seq_q, kv_len0, scale, k1=None, v1=None, kv_len1=0, **kw: 4.0 * heads * seq_q * (kv_len0 + kv_len1) * 64)
+def attention_peer(q, k0, v0, peer_ptrs, my_rank, ldo, heads, seq_q, kv_len0, softmax_scale, k1=None, v1=None, kv_len1=0,
+                   out_scale=1.0):
+    check(lib().vp_attention_peer(_p(q, BF16, "attn.q"), _p(k0, BF16, "attn.k"), _p(v0, BF16, "attn.v"), kv_len0, _p(k1, BF16),
+                                  _p(v1, BF16), kv_len1, _ptr_array(peer_ptrs), len(peer_ptrs), my_rank, ldo, heads, seq_q,
+                                  float(softmax_scale), float(out_scale), _stream()), "vp_attention_peer")
+
+
+@_timed('peer_barrier')
+def peer_barrier(flag_ptrs, my_rank, epoch):
+    check(lib().vp_peer_barrier(_ptr_array(flag_ptrs), len(flag_ptrs), my_rank, epoch & 0xffffffff, _stream()), "vp_peer_barrier")
+
+
 @_timed('a2a_unpack', lambda src, dsts, peers, heads_local, rows_per_peer: 4.0 * len(dsts) * peers * heads_local * rows_per_peer * 64)
 def a2a_unpack_heads(src, dsts, peers, heads_local, rows_per_peer):
     """src [peers][len(dsts)][heads_local][rows_per_peer][64] -> dsts[i] [heads_local][peers * rows_per_peer][64]."""

@@ -14,9 +14,10 @@ Everything here is host-side index arithmetic plus process-group handles; it run
 """
 from __future__ import annotations
 
+import os
 import threading
 from dataclasses import dataclass
-from typing import Optional, Tuple
+from typing import List, Optional, Tuple
 
 
 @dataclass(frozen=True)
@@ -107,10 +108,14 @@ class Runtime:
     """Process-group handles of one rank.  `world_group` spans every rank (final gather), `sp_group` the ranks that share
     this rank's sequence (the per-attention all-to-alls)."""
 
-    def __init__(self, plan: Plan, sp_group=None, world_group=None):
+    def __init__(self, plan: Plan, sp_group=None, world_group=None, p2p: Optional[bool] = None):
         self.plan = plan
         self.sp_group = sp_group
         self.world_group = world_group
+        # p2p: fuse the Ulysses all-to-alls into the producing kernels' epilogues as stores into peer memory (NVLink);
+        # VP_B200_P2P=0 keeps the NCCL all-to-all path
+        self.p2p = (os.environ.get("VP_B200_P2P", "1") != "0") if p2p is None else p2p
+        self._keep = []            # peer storages opened through CUDA IPC must outlive the pointers handed out
 
     def shard(self, seq: int, text: int, heads: int) -> Shard:
         return Shard(self.plan.sp, self.plan.sp_rank, seq, text, heads)
@@ -127,6 +132,39 @@ class Runtime:
         """`out` = concatenation over all ranks (rank order) of `inp`."""
         import torch.distributed as dist
         dist.all_gather_into_tensor(out.view(-1), inp.view(-1), group=self.world_group)
+
+
+    # ---- peer memory (CUDA IPC through torch's storage sharing; plumbing only, the kernels do the stores) ----------------
+    def share(self, t) -> List[int]:
+        """Device pointers, by sequence-parallel rank, to the tensor each rank passed in this (collective) call.  Every
+        rank must pass a tensor of the same shape; the local entry is t.data_ptr()."""
+        import torch
+        import torch.distributed as dist
+        st = t.untyped_storage()
+        info = (st._share_cuda_(), t.storage_offset() * t.element_size())
+        infos = [None] * self.plan.sp
+        dist.all_gather_object(infos, info, group=self.sp_group)
+        ptrs = []
+        for r, (inf, off) in enumerate(infos):
+            if r == self.plan.sp_rank:
+                ptrs.append(t.data_ptr())
+            else:
+                peer = torch.UntypedStorage._new_shared_cuda(*inf)
+                self._keep.append(peer)
+                ptrs.append(peer.data_ptr() + off)
+        return ptrs
+
+    def ready(self) -> None:
+        """Collective: everything the ranks did to the shared buffers so far (zeroing the flags) is complete everywhere."""
+        import torch
+        import torch.distributed as dist
+        torch.cuda.synchronize()
+        dist.barrier(group=self.sp_group)
+
+    def peer_barrier(self, flag_ptrs: List[int], epoch: int) -> None:
+        """Device-side barrier of the sequence-parallel group on the current stream (include/vp_b200.h vp_peer_barrier)."""
+        from . import ops
+        ops.peer_barrier(flag_ptrs, self.plan.sp_rank, epoch)
 
 
 _tls = threading.local()      # per thread, so that tests can run several virtual ranks of one process side by side
