@@ -117,6 +117,13 @@ int vp_attention_peer(const void* q, const void* k0, const void* v0, int kv_len0
                       void* const* peer_out, int peers, int my_rank, int ldo, int heads, int seq_q, float softmax_scale,
                       float out_scale, void* stream);
 int vp_peer_barrier(void* const* peer_flags, int peers, int my_rank, unsigned int epoch, void* stream);
+/* Peer-visible device memory (host calls, synchronous): vp_peer_alloc = cudaMalloc + zero fill + CUDA IPC export (64-byte
+ * handle, to be sent to the other ranks of the node by any means); vp_peer_open maps a peer's handle into the calling
+ * process's current device with peer access enabled; vp_peer_close / vp_peer_free undo them. */
+int vp_peer_alloc(long long bytes, void** ptr, unsigned char* handle64);
+int vp_peer_open(const unsigned char* handle64, void** ptr);
+int vp_peer_close(void* ptr);
+int vp_peer_free(void* ptr);
 
 /* Ulysses receive side (NCCL path): src [peers][slots][heads_local][rows_per_peer][64] (what the all-to-all delivers when every peer
  * sent its vp_gemm_qkv destination block) -> dst[slot] [heads_local][peers * rows_per_peer][64], the layout vp_attention

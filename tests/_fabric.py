@@ -23,15 +23,16 @@ class ThreadRuntime(parallel.Runtime):
         self._n_share = 0
 
     # peer memory: the virtual ranks live in one process on one device, so a "peer pointer" is a plain device pointer
-    def share(self, t):
+    def alloc_shared(self, nbytes, device):
         f, pl = self.fabric, self.plan
         key = ("share", self._n_share)
         self._n_share += 1
+        t = torch.zeros(nbytes, dtype=torch.uint8, device=device)
         f.box[(key, pl.rank)] = t
         f.barrier.wait()
         ptrs = [f.box[(key, r)].data_ptr() for r in pl.sp_ranks()]
         f.barrier.wait()
-        return ptrs
+        return t, ptrs
 
     def ready(self):
         self._sync()

@@ -87,3 +87,21 @@ def test_sharded_inputs_are_validated():
         return True
 
     assert all(run_virtual_ranks(2, rank_fn))
+
+
+def test_peer_buffer_is_zeroed_device_memory_viewed_without_copy():
+    from videopainter_b200 import ops
+    buf = ops.PeerBuffer(1 << 20, torch.device("cuda", 0))
+    t = buf.tensor
+    assert t.is_cuda and t.dtype == torch.uint8 and t.numel() == 1 << 20 and t.data_ptr() == buf.ptr
+    assert int(t.sum()) == 0 and len(buf.handle) == 64
+    v = t.view(BF16).view(-1, 64)
+    v.fill_(1.0)
+    assert float(t.view(BF16).float().sum()) == (1 << 19)
+    # a single-rank peer barrier returns immediately (its own flag)
+    flags = ops.PeerBuffer(64, torch.device("cuda", 0))
+    ops.peer_barrier([flags.ptr], 0, 1)
+    ops.peer_barrier([flags.ptr], 0, 2)
+    torch.cuda.synchronize()
+    assert int(flags.tensor.view(torch.int32)[0]) == 2
+    buf.free(); flags.free()

@@ -34,6 +34,10 @@ SIGNATURES = {
     "vp_attention_peer": [_c_void_p, _c_void_p, _c_void_p, _i, _c_void_p, _c_void_p, _i, _c_void_p, _i, _i, _i, _i, _i, _f, _f,
                           _c_void_p],
     "vp_peer_barrier": [_c_void_p, _i, _i, C.c_uint, _c_void_p],
+    "vp_peer_alloc": [_ll, _c_void_p, _c_void_p],
+    "vp_peer_open": [_c_void_p, _c_void_p],
+    "vp_peer_close": [_c_void_p],
+    "vp_peer_free": [_c_void_p],
     "vp_a2a_unpack_heads": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _i, _i, _i, _i, _c_void_p],
     "vp_attention": [_c_void_p, _c_void_p, _c_void_p, _i, _c_void_p, _c_void_p, _i, _c_void_p, _i, _i, _i, _i, _f, _f, _i,
                      _c_void_p],

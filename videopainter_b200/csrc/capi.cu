@@ -225,6 +225,42 @@ int vp_attention_peer(const void* q, const void* k0, const void* v0, int kv_len0
   return launch_attention(q, k0, v0, k1, v1, p, (cudaStream_t)stream);
 }
 
+int vp_peer_alloc(long long bytes, void** ptr, unsigned char* handle64) {
+  VP_REQUIRE(bytes > 0 && ptr && handle64, VP_ERR_BAD_SHAPE, "peer_alloc: bad arguments");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  void* p = nullptr;
+  VP_CHECK_CUDA(cudaMalloc(&p, (size_t)bytes));
+  VP_CHECK_CUDA(cudaMemset(p, 0, (size_t)bytes));
+  VP_CHECK_CUDA(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  VP_CHECK_CUDA(cudaIpcGetMemHandle(&h, p));
+  memcpy(handle64, &h, 64);
+  *ptr = p;
+  return VP_OK;
+}
+
+int vp_peer_open(const unsigned char* handle64, void** ptr) {
+  VP_REQUIRE(handle64 && ptr, VP_ERR_BAD_SHAPE, "peer_open: bad arguments");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void* p = nullptr;
+  VP_CHECK_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));   // maps into the CURRENT device's context
+  *ptr = p;
+  return VP_OK;
+}
+
+int vp_peer_close(void* ptr) {
+  VP_REQUIRE(ptr, VP_ERR_BAD_SHAPE, "peer_close: null pointer");
+  VP_CHECK_CUDA(cudaIpcCloseMemHandle(ptr));
+  return VP_OK;
+}
+
+int vp_peer_free(void* ptr) {
+  VP_REQUIRE(ptr, VP_ERR_BAD_SHAPE, "peer_free: null pointer");
+  VP_CHECK_CUDA(cudaFree(ptr));
+  return VP_OK;
+}
+
 int vp_peer_barrier(void* const* peer_flags, int peers, int my_rank, unsigned int epoch, void* stream) {
   VP_REQUIRE(peer_flags && peers >= 1 && peers <= 8 && my_rank >= 0 && my_rank < peers, VP_ERR_BAD_SHAPE, "peer_barrier: bad arguments");
   uint32_t* f[8];

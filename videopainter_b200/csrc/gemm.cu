@@ -19,7 +19,9 @@ constexpr int A_BYTES = BM * BK * 2;
 constexpr int B_BYTES = BN * BK * 2;
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int BAR_BYTES = 256;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;   // +1024: manual alignment slack
+constexpr int EPI_STAGE_BYTES = 32 * 128;                              // one head (64 bf16) of 32 rows, per epilogue warp
+constexpr int SMEM_EPI = STAGES * STAGE_BYTES + BAR_BYTES;
+constexpr int SMEM_BYTES = SMEM_EPI + 4 * EPI_STAGE_BYTES + 1024;     // +1024: manual alignment slack
 constexpr int NUM_THREADS = 256;
 constexpr uint32_t TMEM_COLS = 512;
 
@@ -99,8 +101,39 @@ __device__ __forceinline__ void epilogue_cols32(const GemmParams& p, const uint3
 }
 
 // ---- QKV epilogue on one head (64 accumulator columns) of one row ----------------------------------------------
-__device__ __forceinline__ void ln64_rope_store(const float* x, float pre, const __nv_bfloat16* w, const __nv_bfloat16* bia,
-                                                float eps, const float* cosr, const float* sinr, __nv_bfloat16* dst) {
+// Each thread owns one 128-byte output row (one head of one token).  Storing it directly would make every warp-wide
+// store touch 32 different lines with 16 bytes each — harmless behind the local L2, but over NVLink (peer mode) every
+// such piece travels as its own small packet.  So the warp transposes through 4 KB of XOR-swizzled shared memory
+// (conflict-free both ways) and then writes whole 128-byte lines: 8 lanes per row, 4 rows per store instruction.
+__device__ __forceinline__ void warp_store_rows128(uint8_t* stage, int lane, const uint4 (&c)[8], __nv_bfloat16* dst) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(stage + lane * 128 + ((i ^ (lane & 7)) << 4)) = c[i];
+  __syncwarp();
+  const unsigned long long d = reinterpret_cast<unsigned long long>(dst);     // 0 = this row is not stored
+  const int cc = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * 4 + (lane >> 3);
+    const uint4 v = *reinterpret_cast<const uint4*>(stage + r * 128 + ((cc ^ (r & 7)) << 4));
+    const unsigned long long dr = __shfl_sync(0xffffffffu, d, r);
+    if (dr) *reinterpret_cast<uint4*>(dr + (cc << 4)) = v;
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ void pack_bf16x32(const float* f, uint4* u) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    u[i].x = pack_bf16(f[i * 8 + 0], f[i * 8 + 1]);
+    u[i].y = pack_bf16(f[i * 8 + 2], f[i * 8 + 3]);
+    u[i].z = pack_bf16(f[i * 8 + 4], f[i * 8 + 5]);
+    u[i].w = pack_bf16(f[i * 8 + 6], f[i * 8 + 7]);
+  }
+}
+
+// LayerNorm(64) of (x * pre) with affine (w, bia), optional interleaved-pair RoPE, packed to bf16 in `out` (8 x 16 bytes)
+__device__ __forceinline__ void ln64_rope_pack(const float* x, float pre, const __nv_bfloat16* w, const __nv_bfloat16* bia,
+                                               float eps, const float* cosr, const float* sinr, uint4 (&out)[8]) {
   float mean = 0.f;
 #pragma unroll
   for (int j = 0; j < 64; ++j) mean += x[j];
@@ -132,11 +165,13 @@ __device__ __forceinline__ void ln64_rope_store(const float* x, float pre, const
         y[j * 4 + 3] = a3 * cv.w + a2 * sv.w;
       }
     }
-    store_bf16x32(dst + c * 32, y);
+    pack_bf16x32(y, &out[c * 4]);
   }
 }
 
-__device__ __forceinline__ void epilogue_qkv_head(const GemmParams& p, const uint32_t* acc, int m, int b, int s, int n0) {
+// Runs warp-wide (all 32 lanes, also those whose row is out of range: row_ok = false stores nothing).
+__device__ __forceinline__ void epilogue_qkv_head(const GemmParams& p, const uint32_t* acc, bool row_ok, int m, int b, int s, int n0,
+                                                  uint8_t* stage, int lane) {
   float x[64];
   load_bf16x32(p.bias + n0, x);
   load_bf16x32(p.bias + n0 + 32, x + 32);
@@ -144,41 +179,47 @@ __device__ __forceinline__ void epilogue_qkv_head(const GemmParams& p, const uin
   for (int j = 0; j < 64; ++j) x[j] += __uint_as_float(acc[j]);
   const int which = n0 / p.d_model + p.qkv_first;      // 0 = Q, 1 = K, 2 = V
   const int head = (n0 % p.d_model) >> 6;
-  const float rs = p.row_scale ? p.row_scale[m] : 1.0f;
+  const float rs = (p.row_scale && row_ok) ? p.row_scale[m] : 1.0f;
   const int dest = head / p.heads_per_dest, hl = head - dest * p.heads_per_dest;
   long long off = dest * p.dest_stride + (((long long)b * p.heads_per_dest + hl) * p.rows_per_batch + s) * 64;
   if (p.peer_base[0]) {           // store into the destination rank's memory (P2P): offset relative to the local twin buffer
     off = (p.peer_base[dest] - p.local_base) + ((long long)hl * p.peer_seq + p.peer_row_off + s) * 64;
   }
+  uint4 out[8];
   if (which == 2) {
     float y[32];
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) y[j] = x[c * 32 + j] * rs;
-      store_bf16x32(p.v_out + off + c * 32, y);
+      pack_bf16x32(y, &out[c * 4]);
     }
+    warp_store_rows128(stage, lane, out, row_ok ? p.v_out + off : nullptr);
     if (p.v2_out) {
-      const float mk = p.mask2[m] ? 1.0f : 0.0f;
+      const float mk = (row_ok && p.mask2[m]) ? 1.0f : 0.0f;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) y[j] = x[c * 32 + j] * mk;
-        store_bf16x32(p.v2_out + off + c * 32, y);
+        pack_bf16x32(y, &out[c * 4]);
       }
+      warp_store_rows128(stage, lane, out, row_ok ? p.v2_out + off : nullptr);
     }
     return;
   }
-  const bool rope = p.rope_cos != nullptr && s >= p.text_len;
+  const bool rope = p.rope_cos != nullptr && s >= p.text_len && row_ok;
   const float* cosr = rope ? p.rope_cos + (long long)(s - p.text_len) * 64 : nullptr;
   const float* sinr = rope ? p.rope_sin + (long long)(s - p.text_len) * 64 : nullptr;
   if (which == 0) {
-    ln64_rope_store(x, rs, p.nq_w, p.nq_b, p.qk_eps, cosr, sinr, p.q_out + off);
+    ln64_rope_pack(x, rs, p.nq_w, p.nq_b, p.qk_eps, cosr, sinr, out);
+    warp_store_rows128(stage, lane, out, row_ok ? p.q_out + off : nullptr);
   } else {
-    ln64_rope_store(x, rs, p.nk_w, p.nk_b, p.qk_eps, cosr, sinr, p.k_out + off);
+    ln64_rope_pack(x, rs, p.nk_w, p.nk_b, p.qk_eps, cosr, sinr, out);
+    warp_store_rows128(stage, lane, out, row_ok ? p.k_out + off : nullptr);
     if (p.k2_out) {
-      const float mk = p.mask2[m] ? 1.0f : 0.0f;    // masked-out keys become RoPE(norm_k.bias): AP:2255, 2272, 2281
-      ln64_rope_store(x, mk, p.nk_w, p.nk_b, p.qk_eps, cosr, sinr, p.k2_out + off);
+      const float mk = (row_ok && p.mask2[m]) ? 1.0f : 0.0f;    // masked-out keys become RoPE(norm_k.bias): AP:2255, 2272, 2281
+      ln64_rope_pack(x, mk, p.nk_w, p.nk_b, p.qk_eps, cosr, sinr, out);
+      warp_store_rows128(stage, lane, out, row_ok ? p.k2_out + off : nullptr);
     }
   }
 }
@@ -308,7 +349,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           tmem_ld_x32(taddr + hc * 64, r);
           tmem_ld_x32(taddr + hc * 64 + 32, r + 32);
           tmem_wait_ld();
-          if (row_ok) epilogue_qkv_head(p, r, m, b, s, n0);
+          epilogue_qkv_head(p, r, row_ok, m, b, s, n0, smem + SMEM_EPI + (warp - 4) * EPI_STAGE_BYTES, lane);
         }
       } else {
 #pragma unroll 1

@@ -161,7 +161,8 @@ class _Workspace:
         # peer mode: q, k, v, k2, v2 are the five slots of one buffer that the peers' QKV epilogues write into
         self.peer = rt is not None and rt.p2p and P > 1
         if self.peer:
-            self.qkv_sym = e(5, Hl, S, 64)
+            raw, self.ptrs_qkv = rt.alloc_shared(5 * Hl * S * 64 * 2, device)
+            self.qkv_sym = raw.view(BF16).view(5, Hl, S, 64)
             self.q, self.k, self.v, self.k2, self.v2 = (self.qkv_sym[i].unsqueeze(0) for i in range(5))
         else:
             self.q = e(B, Hl, S, 64)
@@ -182,16 +183,16 @@ class _Workspace:
         # Ulysses exchange buffers (allocated on first use)
         self._send = {}
         self._recv = {}
-        self.ao_recv = e(P, R, Hl * 64) if P > 1 else None
         self.xfull = None
         if self.peer:
             self.rt = rt
-            self.flags = torch.zeros(16, dtype=torch.int32, device=device)
+            raw, self.ptrs_ao = rt.alloc_shared(P * R * Hl * 64 * 2, device)
+            self.ao_recv = raw.view(BF16).view(P, R, Hl * 64)
+            self.flags, self.ptrs_flags = rt.alloc_shared(64, device)
             self.epoch = 0
-            self.ptrs_qkv = rt.share(self.qkv_sym)
-            self.ptrs_ao = rt.share(self.ao_recv)
-            self.ptrs_flags = rt.share(self.flags)
             rt.ready()
+        else:
+            self.ao_recv = e(P, R, Hl * 64) if P > 1 else None
 
     def peer_sync(self):
         """All peer stores issued so far by every rank of the group are visible to every rank after this point of the

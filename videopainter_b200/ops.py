@@ -238,3 +238,37 @@ def mask_pool(mask, out, bf, h, w):
 def unpatchify(proj, out, bf, c, h, w):
     check(lib().vp_unpatchify(_p(proj, BF16, "unpatchify.proj"), bf, c, h, w, _p(out, BF16), _stream()), "vp_unpatchify")
     return out
+
+
+# ---- peer-visible device memory (CUDA IPC) ----------------------------------------------------------------------------
+class PeerBuffer:
+    """`nbytes` of zero-filled device memory allocated by the library (cudaMalloc, so that it can be exported through CUDA
+    IPC) and viewed as a torch uint8 tensor without copying."""
+
+    def __init__(self, nbytes: int, device):
+        import ctypes as C
+        ptr = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        with torch.cuda.device(device):
+            check(lib().vp_peer_alloc(nbytes, C.byref(ptr), handle), "vp_peer_alloc")
+        self.ptr, self.nbytes, self.handle = ptr.value, nbytes, bytes(handle)
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (self.ptr, False), "version": 2,
+                                         "strides": None}
+        self.tensor = torch.as_tensor(self, device=device)
+        assert self.tensor.data_ptr() == self.ptr
+
+    def free(self):
+        if self.ptr:
+            self.tensor = None
+            check(lib().vp_peer_free(self.ptr), "vp_peer_free")
+            self.ptr = None
+
+
+def peer_open(handle: bytes, device) -> int:
+    """Map a peer rank's PeerBuffer (its 64-byte IPC handle) into this process; returns the device pointer."""
+    import ctypes as C
+    ptr = C.c_void_p()
+    buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+    with torch.cuda.device(device):
+        check(lib().vp_peer_open(buf, C.byref(ptr)), "vp_peer_open")
+    return ptr.value

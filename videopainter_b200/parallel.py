@@ -135,24 +135,17 @@ class Runtime:
 
 
     # ---- peer memory (CUDA IPC through torch's storage sharing; plumbing only, the kernels do the stores) ----------------
-    def share(self, t) -> List[int]:
-        """Device pointers, by sequence-parallel rank, to the tensor each rank passed in this (collective) call.  Every
-        rank must pass a tensor of the same shape; the local entry is t.data_ptr()."""
-        import torch
+    def alloc_shared(self, nbytes: int, device):
+        """Collective over the sequence-parallel group: every rank allocates `nbytes` of zero-filled peer-visible memory.
+        Returns (local uint8 tensor, device pointers to every rank's buffer by rank; the local entry is the tensor's)."""
         import torch.distributed as dist
-        st = t.untyped_storage()
-        info = (st._share_cuda_(), t.storage_offset() * t.element_size())
-        infos = [None] * self.plan.sp
-        dist.all_gather_object(infos, info, group=self.sp_group)
-        ptrs = []
-        for r, (inf, off) in enumerate(infos):
-            if r == self.plan.sp_rank:
-                ptrs.append(t.data_ptr())
-            else:
-                peer = torch.UntypedStorage._new_shared_cuda(*inf)
-                self._keep.append(peer)
-                ptrs.append(peer.data_ptr() + off)
-        return ptrs
+        from . import ops
+        buf = ops.PeerBuffer(nbytes, device)
+        handles = [None] * self.plan.sp
+        dist.all_gather_object(handles, buf.handle, group=self.sp_group)
+        ptrs = [buf.ptr if r == self.plan.sp_rank else ops.peer_open(h, device) for r, h in enumerate(handles)]
+        self._keep.append(buf)
+        return buf.tensor, ptrs
 
     def ready(self) -> None:
         """Collective: everything the ranks did to the shared buffers so far (zeroing the flags) is complete everywhere."""
