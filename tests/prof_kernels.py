@@ -48,6 +48,11 @@ def main():
     timeit("attention_S17776", lambda: ops.attention(q, k, v, ao, B, H, S, S, 0.125), 4.0 * B * H * S * S * 64, "tflops")
     timeit("attention_2seg", lambda: ops.attention(q, k, v, ao, B, H, S, S, 0.125, k1=k, v1=v, kv_len1=S),
            8.0 * B * H * S * S * 64, "tflops")
+    # the peer-memory instantiation (Ulysses output stores), here with a single "peer": same work, batch folded into heads
+    ao1 = torch.empty(1, S, B * H * 64, dtype=BF16, device=dev)
+    q1, k1, v1 = q.view(1, B * H, S, 64), k.view(1, B * H, S, 64), v.view(1, B * H, S, 64)
+    timeit("attention_peer_S17776", lambda: ops.attention_peer(q1, k1, v1, [ao1.data_ptr()], 0, B * H * 64, B * H, S, S, 0.125),
+           4.0 * B * H * S * S * 64, "tflops")
     x = rn(M, D)
     w_qkv, b_qkv = rn(3 * D, D, sc=0.02), rn(3 * D)
     nq = (rn(64), rn(64))

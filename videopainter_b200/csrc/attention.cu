@@ -163,6 +163,9 @@ struct Bars {
   uint32_t tmem_slot;
 };
 
+// PEER = true: the output rows are stored into the owning ranks' buffers (Ulysses over NVLink peer memory).  Two
+// instantiations on purpose: the main loop's code generation is sensitive to everything that shares its registers.
+template <bool PEER>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k0,
                 const __grid_constant__ CUtensorMap tmap_v0, const __grid_constant__ CUtensorMap tmap_k1,
@@ -380,28 +383,55 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     tmem_ld_x32(tO, o);
     tmem_wait_ld();
     const int q_row = q0 + t * BQ + row;
-    if (q_row < p.seq_q) {
-      const float inv = p.out_scale / total;
-      const int b = bh / p.heads, h = bh - b * p.heads;
-      __nv_bfloat16* dst = p.out + ((long long)b * p.seq_q + q_row) * p.ldo + h * DH + half * 32;
-      if (p.peer_out[0]) {                                       // P2P store into the rank that owns this token row
-        const int dest = q_row / p.peer_rows;
-        dst = p.peer_out[dest] + ((long long)p.peer_src * p.peer_rows + (q_row - dest * p.peer_rows)) * p.ldo + h * DH + half * 32;
+    const bool row_ok = q_row < p.seq_q;
+    const float inv = p.out_scale / total;
+    const int b = bh / p.heads, h = bh - b * p.heads;
+    __nv_bfloat16* dst = p.out + ((long long)b * p.seq_q + q_row) * p.ldo + h * DH + half * 32;
+    if (PEER && row_ok) {                                        // P2P store into the rank that owns this token row
+      const int dest = q_row / p.peer_rows;
+      dst = p.peer_out[dest] + ((long long)p.peer_src * p.peer_rows + (q_row - dest * p.peer_rows)) * p.ldo + h * DH + half * 32;
+    }
+    if (!PEER) {                                                 // local output: direct 16-byte stores (L2 merges the lines)
+      if (row_ok) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float f[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(o[i * 8 + e]) * inv;
+          if (p.accumulate) {                                    // read-modify-write in fp32 (previous-window blend)
+            const uint4 old = *reinterpret_cast<const uint4*>(dst + i * 8);
+            f[0] += bf16_lo(old.x); f[1] += bf16_hi(old.x); f[2] += bf16_lo(old.y); f[3] += bf16_hi(old.y);
+            f[4] += bf16_lo(old.z); f[5] += bf16_hi(old.z); f[6] += bf16_lo(old.w); f[7] += bf16_hi(old.w);
+          }
+          uint4 u;
+          u.x = pack_bf16(f[0], f[1]); u.y = pack_bf16(f[2], f[3]);
+          u.z = pack_bf16(f[4], f[5]); u.w = pack_bf16(f[6], f[7]);
+          *reinterpret_cast<uint4*>(dst + i * 8) = u;
+        }
       }
+    } else {
+      // Peer output.  Each thread holds 64 bytes of its row.  The warp transposes through 2 KB of swizzled shared memory (the Q tile of
+      // this query tile: every MMA that read it has completed) so that 4 lanes write one row's 64 bytes together —
+      // 8 rows x 64 B per store instruction instead of 32 rows x 16 B, which matters for the NVLink peer stores.
+      uint8_t* stage = smem + SMEM_Q + t * TILE_BYTES + (half * 4 + quad) * 2048;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        float f[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(o[i * 8 + e]) * inv;
-        if (p.accumulate) {
-          const uint4 old = *reinterpret_cast<const uint4*>(dst + i * 8);
-          f[0] += bf16_lo(old.x); f[1] += bf16_hi(old.x); f[2] += bf16_lo(old.y); f[3] += bf16_hi(old.y);
-          f[4] += bf16_lo(old.z); f[5] += bf16_hi(old.z); f[6] += bf16_lo(old.w); f[7] += bf16_hi(old.w);
-        }
         uint4 u;
-        u.x = pack_bf16(f[0], f[1]); u.y = pack_bf16(f[2], f[3]);
-        u.z = pack_bf16(f[4], f[5]); u.w = pack_bf16(f[6], f[7]);
-        *reinterpret_cast<uint4*>(dst + i * 8) = u;
+        u.x = pack_bf16(__uint_as_float(o[i * 8 + 0]) * inv, __uint_as_float(o[i * 8 + 1]) * inv);
+        u.y = pack_bf16(__uint_as_float(o[i * 8 + 2]) * inv, __uint_as_float(o[i * 8 + 3]) * inv);
+        u.z = pack_bf16(__uint_as_float(o[i * 8 + 4]) * inv, __uint_as_float(o[i * 8 + 5]) * inv);
+        u.w = pack_bf16(__uint_as_float(o[i * 8 + 6]) * inv, __uint_as_float(o[i * 8 + 7]) * inv);
+        *reinterpret_cast<uint4*>(stage + lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4)) = u;
+      }
+      __syncwarp();
+      const unsigned long long d = row_ok ? reinterpret_cast<unsigned long long>(dst) : 0ull;
+      const int cc = lane & 3;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = i * 8 + (lane >> 2);
+        const uint4 v = *reinterpret_cast<const uint4*>(stage + r * 64 + ((cc ^ ((r >> 1) & 3)) << 4));
+        const unsigned long long dr = __shfl_sync(0xffffffffu, d, r);
+        if (dr) *reinterpret_cast<uint4*>(dr + (cc << 4)) = v;
       }
     }
   } else {
@@ -524,7 +554,8 @@ int launch_attention(const void* q, const void* k0, const void* v0, const void* 
              "attention: peer output needs batch 1 and no accumulation");
   static bool configured = false;
   if (!configured) {
-    VP_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    VP_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    VP_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     configured = true;
   }
   const long long bh = (long long)p.batch * p.heads;
@@ -541,7 +572,8 @@ int launch_attention(const void* q, const void* k0, const void* v0, const void* 
     mv1 = mv0;
   }
   dim3 grid((p.seq_q + 2 * BQ - 1) / (2 * BQ), (unsigned)bh);
-  attn_fwd_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mq, mk0, mv0, mk1, mv1, p);
+  if (p.peer_out[0]) attn_fwd_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mq, mk0, mv0, mk1, mv1, p);
+  else attn_fwd_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mq, mk0, mv0, mk1, mv1, p);
   VP_CHECK_CUDA(cudaGetLastError());
   return VP_OK;
 }
