@@ -11,6 +11,7 @@ Data layout in HBM
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass, field
 from typing import Any, Dict, List, Optional, Sequence, Tuple
 
@@ -20,6 +21,9 @@ from . import ops, parallel
 from .parallel import Shard, qkv_dest_stride, send_block_shape
 
 BF16 = torch.bfloat16
+# Ulysses output exchange in peer mode: "kernel" = the attention epilogue stores into the owners' buffers (its own kernel
+# instantiation, whose main loop compiles ~8 % slower), default = unchanged attention kernel + copy-engine scatter
+_PEER_ATTN_STORES = os.environ.get("VP_B200_P2P_ATTN", "copy") == "kernel"
 
 
 @dataclass
@@ -336,7 +340,11 @@ def _block(pm: PackedModel, blk: PackedBlock, ws: _Workspace, x_in: torch.Tensor
     def attend(k1=None, v1=None, kv_len1=0):
         if peer:
             ws.peer_sync()                                            # every rank's q / k / v rows have landed
-            ops.attention_peer(ws.q, ws.k, ws.v, ws.ptrs_ao, sh.sp_rank, ldo, Hl, S, S, scale, k1=k1, v1=v1, kv_len1=kv_len1)
+            if _PEER_ATTN_STORES:                                     # output rows stored by the kernel's own epilogue
+                ops.attention_peer(ws.q, ws.k, ws.v, ws.ptrs_ao, sh.sp_rank, ldo, Hl, S, S, scale, k1=k1, v1=v1, kv_len1=kv_len1)
+            else:                                                     # plain kernel + copy-engine scatter (measured faster)
+                ops.attention(ws.q, ws.k, ws.v, ws.ao, B, Hl, S, S, scale, k1=k1, v1=v1, kv_len1=kv_len1, ldo=ldo)
+                ws.rt.scatter(ws.ao, ws.ptrs_ao, R * ldo * 2)
             ws.peer_sync()                                            # every rank's output rows have landed in ao_recv
         else:
             ops.attention(ws.q, ws.k, ws.v, ws.ao, B, Hl, S, S, scale, k1=k1, v1=v1, kv_len1=kv_len1, ldo=ldo)

@@ -197,6 +197,12 @@ def attention_peer(q, k0, v0, peer_ptrs, my_rank, ldo, heads, seq_q, kv_len0, so
                                   float(softmax_scale), float(out_scale), _stream()), "vp_attention_peer")
 
 
+@_timed('peer_scatter')
+def peer_scatter(src, peer_ptrs, my_rank, bytes_per_peer):
+    check(lib().vp_peer_scatter(_p(src, name="scatter.src"), _ptr_array(peer_ptrs), len(peer_ptrs), my_rank, bytes_per_peer, _stream()),
+          "vp_peer_scatter")
+
+
 @_timed('peer_barrier')
 def peer_barrier(flag_ptrs, my_rank, epoch):
     check(lib().vp_peer_barrier(_ptr_array(flag_ptrs), len(flag_ptrs), my_rank, epoch & 0xffffffff, _stream()), "vp_peer_barrier")

@@ -154,6 +154,11 @@ class Runtime:
         torch.cuda.synchronize()
         dist.barrier(group=self.sp_group)
 
+    def scatter(self, src, peer_ptrs: List[int], bytes_per_peer: int) -> None:
+        """Chunk d of `src` -> slot sp_rank of rank d's buffer (include/vp_b200.h vp_peer_scatter)."""
+        from . import ops
+        ops.peer_scatter(src, peer_ptrs, self.plan.sp_rank, bytes_per_peer)
+
     def peer_barrier(self, flag_ptrs: List[int], epoch: int) -> None:
         """Device-side barrier of the sequence-parallel group on the current stream (include/vp_b200.h vp_peer_barrier)."""
         from . import ops
