@@ -72,6 +72,10 @@ class PackedModel:
     proj_w: Optional[torch.Tensor] = None; proj_b: Optional[torch.Tensor] = None
     branch_w: List[torch.Tensor] = field(default_factory=list)
     branch_b: List[torch.Tensor] = field(default_factory=list)
+    # all LayerNormZero linears stacked [L * 2 * 6D, time_dim] (norm1 of block 0, norm2 of block 0, norm1 of block 1, ...):
+    # the modulation tables of a whole forward come from ONE weight-streaming launch; the per-block fields are views
+    ada_w: Optional[torch.Tensor] = None
+    ada_b: Optional[torch.Tensor] = None
     workspace: Dict[Any, Any] = field(default_factory=dict)
 
 
@@ -132,9 +136,15 @@ def pack_state_dict(sd: Dict[str, torch.Tensor], dims: Dims, device, lora_scale:
         raise ValueError("only the CogVideoX-5B family (rotary + learned positional table) is supported")
     t1w, t1b = lin("time_embedding.linear_1")
     t2w, t2b = lin("time_embedding.linear_2")
+    ada_w = torch.cat([w for blk in blocks for w in (blk.n1_lin_w, blk.n2_lin_w)], dim=0).contiguous()
+    ada_b = torch.cat([b for blk in blocks for b in (blk.n1_lin_b, blk.n2_lin_b)], dim=0).contiguous()
+    n6 = 6 * D
+    for i, blk in enumerate(blocks):
+        blk.n1_lin_w, blk.n2_lin_w = ada_w[(2 * i) * n6:(2 * i + 1) * n6], ada_w[(2 * i + 1) * n6:(2 * i + 2) * n6]
+        blk.n1_lin_b, blk.n2_lin_b = ada_b[(2 * i) * n6:(2 * i + 1) * n6], ada_b[(2 * i + 1) * n6:(2 * i + 2) * n6]
     pm = PackedModel(dims=dims, blocks=blocks, patch_w=pw, patch_b=t(sd["patch_embed.proj.bias"]), kpad=kpad,
                      text_w=tw, text_b=tb, pos=t(sd["patch_embed.pos_embedding"][0]),
-                     t1_w=t1w, t1_b=t1b, t2_w=t2w, t2_b=t2b)
+                     t1_w=t1w, t1_b=t1b, t2_w=t2w, t2_b=t2b, ada_w=ada_w, ada_b=ada_b)
     if dims.is_branch:
         for i in range(dims.num_layers):
             w, b = lin(f"branch_blocks.{i}")
@@ -177,8 +187,6 @@ class _Workspace:
         self.ao = e(B * S, Hl * 64)                     # attention output, token-major (send buffer of all-to-all #2)
         self.xmid = e(B, R, D)
         self.ffm = e(B * R, 4 * D)
-        self.mod1 = e(B, 6 * D, dtype=torch.float32)
-        self.mod2 = e(B, 6 * D, dtype=torch.float32)
         self.patches = e(B * Sv, pm.kpad)
         self.ping = [None, None]
         self.device = device
@@ -320,7 +328,13 @@ def _qkv(pm, blk, ws, xn, which_first, rope, mask2=None, row_scale=None, masked_
     ops.a2a_unpack_heads(recv, outs, sh.sp, Hl, R)
 
 
-def _block(pm: PackedModel, blk: PackedBlock, ws: _Workspace, x_in: torch.Tensor, x_out: torch.Tensor, emb: torch.Tensor,
+def _ada_tables(pm: PackedModel, emb: torch.Tensor) -> torch.Tensor:
+    """silu(temb) @ W^T + b of every CogVideoXLayerNormZero of the model (NRM:376) in one launch: [B, L * 2 * 6D] fp32; block i
+    uses columns [2i * 6D, (2i + 1) * 6D) for norm1 and the next 6D for norm2."""
+    return ops.gemv(emb, pm.ada_w, pm.ada_b, act_silu=True)
+
+
+def _block(pm: PackedModel, blk: PackedBlock, ws: _Workspace, x_in: torch.Tensor, x_out: torch.Tensor, mods,
            rope, B, S, St, Sv, resample_mask_u8=None, prev=None, prev_w=None, prev_mask=None, inject=None, inject_mask=None,
            group=None):
     """CogVideoXBlock.forward T3D:125-184 (+ branch injection T3D:596-609 fused into the FFN-2 epilogue).  x_in / x_out are
@@ -330,8 +344,8 @@ def _block(pm: PackedModel, blk: PackedBlock, ws: _Workspace, x_in: torch.Tensor
     D, Hl, R = d.D, sh.heads_local, sh.rows
     M = B * R
     OFF1 = (0, D, 3 * D, 4 * D)       # shift, scale (video) / enc_shift, enc_scale (text) inside the 6D table
-    ops.gemv(emb, blk.n1_lin_w, blk.n1_lin_b, act_silu=True, out=ws.mod1)
-    ops.ln_modulate(x_in, R, 0, ws.xn, B, R, D, blk.n1_w, blk.n1_b, d.eps, ws.mod1, OFF1, St)
+    mod1, mod2 = mods                 # [B, 6D] fp32 views (row stride = the whole table)
+    ops.ln_modulate(x_in, R, 0, ws.xn, B, R, D, blk.n1_w, blk.n1_b, d.eps, mod1, OFF1, St)
     use_prev = prev is not None and prev_w is not None and prev_w > 0.0
     scale = 1.0 / math.sqrt(d.head_dim)
     ldo = Hl * 64
@@ -358,7 +372,7 @@ def _block(pm: PackedModel, blk: PackedBlock, ws: _Workspace, x_in: torch.Tensor
         _qkv(pm, blk, ws, ws.xn, 0, rope, group=group)
         if use_prev:
             # T3D:141-146: norm1 of the previous window's states with the current timestep embedding
-            ops.ln_modulate(prev, R, 0, ws.xn, B, R, D, blk.n1_w, blk.n1_b, d.eps, ws.mod1, OFF1, St)
+            ops.ln_modulate(prev, R, 0, ws.xn, B, R, D, blk.n1_w, blk.n1_b, d.eps, mod1, OFF1, St)
             k2, v2 = ws.second_kv()
             if d.resample:                                            # AP:2247-2252, one softmax over 2S keys
                 _qkv(pm, blk, ws, ws.xn, 1, rope, row_scale=prev_mask, group=group)
@@ -383,17 +397,16 @@ def _block(pm: PackedModel, blk: PackedBlock, ws: _Workspace, x_in: torch.Tensor
         ao = ws.ao_recv
         a_kw = dict(lda=ldo, a_k_chunk=ldo, a_chunk_stride=R * ldo)
     ops.gemm_gate_residual(ao, blk.out_w, blk.out_b, ws.xmid, M, D, D, rows_per_batch=R, out_batch_rows=R, out_row_offset=0,
-                           res=x_in, res_batch_rows=R, res_row_offset=0, gate=ws.mod1, gate_video_off=2 * D,
+                           res=x_in, res_batch_rows=R, res_row_offset=0, gate=mod1, gate_video_off=2 * D,
                            gate_text_off=5 * D, text_len=St, **a_kw)
-    ops.gemv(emb, blk.n2_lin_w, blk.n2_lin_b, act_silu=True, out=ws.mod2)
-    ops.ln_modulate(ws.xmid, R, 0, ws.xn, B, R, D, blk.n2_w, blk.n2_b, d.eps, ws.mod2, OFF1, St)
+    ops.ln_modulate(ws.xmid, R, 0, ws.xn, B, R, D, blk.n2_w, blk.n2_b, d.eps, mod2, OFF1, St)
     ops.gemm_gelu(ws.xn, blk.ff1_w, blk.ff1_b, ws.ffm, M, 4 * D, D)
     inj_kw = {}
     if inject is not None:
         inj_kw = dict(inject=inject, inject_batch_stride=inject.stride(0), ldi=inject.stride(1), inject_mask=inject_mask,
                       video_len=Sv)
     ops.gemm_gate_residual(ws.ffm, blk.ff2_w, blk.ff2_b, x_out, M, D, 4 * D, rows_per_batch=R, out_batch_rows=R, out_row_offset=0,
-                           res=ws.xmid, res_batch_rows=R, res_row_offset=0, gate=ws.mod2, gate_video_off=2 * D,
+                           res=ws.xmid, res_batch_rows=R, res_row_offset=0, gate=mod2, gate_video_off=2 * D,
                            gate_text_off=5 * D, text_len=St, **inj_kw)
 
 
@@ -462,8 +475,11 @@ def branch_forward(pm: PackedModel, hidden_states: torch.Tensor, encoder_hidden_
     _embed_sharded(pm, ws, x[0], encoder_hidden_states[bs].to(BF16).contiguous(), hidden_states[bs].to(BF16).contiguous(),
                    branch_cond[bs].to(BF16).contiguous(), B, Fr, H, W, St, Sv)
     outs = []
+    tab = _ada_tables(pm, emb)
+    n6 = 6 * d.D
     for i, blk in enumerate(pm.blocks):
-        _block(pm, blk, ws, x[i], x[i + 1], emb, rope, B, S, sh.text_rows, sh.video_rows, group=group)
+        mods = (tab[:, (2 * i) * n6:(2 * i + 1) * n6], tab[:, (2 * i + 1) * n6:(2 * i + 2) * n6])
+        _block(pm, blk, ws, x[i], x[i + 1], mods, rope, B, S, sh.text_rows, sh.video_rows, group=group)
     for i in range(d.num_layers):
         o = torch.empty(B, sh.video_rows, d.D, dtype=BF16, device=dev)
         # branch_blocks[i] on the video rows only (BR:416-421); text rows are dropped by the negative row offset
@@ -564,7 +580,10 @@ def transformer_forward(pm: PackedModel, hidden_states: torch.Tensor, encoder_hi
             samples.append(s)
     interval = int(math.ceil(L / len(samples))) if samples else 1                  # T3D:598-599
 
+    tab = _ada_tables(pm, emb)
+    n6 = 6 * D
     for i, blk in enumerate(pm.blocks):
+        mods = (tab[:, (2 * i) * n6:(2 * i + 1) * n6], tab[:, (2 * i + 1) * n6:(2 * i + 2) * n6])
         inject = None
         if samples is not None:
             if not add_first:
@@ -579,7 +598,7 @@ def transformer_forward(pm: PackedModel, hidden_states: torch.Tensor, encoder_hi
                 if rt is not None and prev.shape == (Bg, S, D):
                     prev = prev[bs, sh.row0:sh.row0 + R]
                 prev = prev.contiguous()
-        _block(pm, blk, ws, xs[i], xs[i + 1], emb, rope, B, S, St_l, Sv_l, resample_mask_u8=rm_local,
+        _block(pm, blk, ws, xs[i], xs[i + 1], mods, rope, B, S, St_l, Sv_l, resample_mask_u8=rm_local,
                prev=prev, prev_w=prev_w if prev is not None else None, prev_mask=prev_mask_f, inject=inject,
                inject_mask=mask_local if inject is not None else None, group=group)
 

@@ -111,7 +111,7 @@ def ln_modulate(x: torch.Tensor, x_batch_rows: int, x_row_offset: int, y: torch.
     """offs = (shift_video, scale_video, shift_text, scale_text) element offsets into one batch row of `mod`."""
     check(lib().vp_ln_modulate(_p(x, BF16, "ln.x"), x_batch_rows, x_row_offset, _p(y, BF16, "ln.y"), batch, rows_per_batch, dim,
                                _p(gamma, BF16, "ln.gamma"), _p(beta, BF16, "ln.beta"), float(eps),
-                               _p(mod, torch.float32, "ln.mod"), 0 if mod is None else mod.shape[1],
+                               _base(mod, torch.float32), 0 if mod is None else mod.stride(0),
                                offs[0], offs[1], offs[2], offs[3], text_len, _stream()), "vp_ln_modulate")
     return y
 
@@ -147,7 +147,7 @@ def gemm_gate_residual(a, w, bias, out, m, n, k, rows_per_batch, out_batch_rows,
     check(lib().vp_gemm_gate_residual(
         _p(a, BF16, "gemm.a"), lda or k, _p(w, BF16, "gemm.w"), ldw or k, _p(bias, BF16, "gemm.bias"), _p(out, BF16, "gemm.out"),
         n, m, n, k, rows_per_batch, out_batch_rows, out_row_offset, _p(res, BF16, "gemm.res"), n, res_batch_rows, res_row_offset,
-        _p(gate, torch.float32, "gemm.gate"), 0 if gate is None else gate.shape[1], gate_video_off, gate_text_off, text_len,
+        _base(gate, torch.float32), 0 if gate is None else gate.stride(0), gate_video_off, gate_text_off, text_len,
         None if inject is None else inject.data_ptr(), inject_batch_stride, ldi,
         _p(inject_mask, torch.uint8, "gemm.inject_mask"), video_len, a_k_chunk, a_chunk_stride, _stream()),
         "vp_gemm_gate_residual")
