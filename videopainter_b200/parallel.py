@@ -140,9 +140,14 @@ class Runtime:
         Returns (local uint8 tensor, device pointers to every rank's buffer by rank; the local entry is the tensor's)."""
         import torch.distributed as dist
         from . import ops
-        buf = ops.PeerBuffer(nbytes, device)
+        try:
+            buf, err = ops.PeerBuffer(nbytes, device), None
+        except Exception as e:   # noqa: BLE001 - still take part in the collective below, then fail on every rank
+            buf, err = None, e
         handles = [None] * self.plan.sp
-        dist.all_gather_object(handles, buf.handle, group=self.sp_group)
+        dist.all_gather_object(handles, None if buf is None else buf.handle, group=self.sp_group)
+        if any(h is None for h in handles):
+            raise RuntimeError(f"peer-visible allocation failed on a rank of the group ({err})")
         ptrs = [buf.ptr if r == self.plan.sp_rank else ops.peer_open(h, device) for r, h in enumerate(handles)]
         self._keep.append(buf)
         return buf.tensor, ptrs
@@ -183,7 +188,31 @@ def init(world: Optional[int] = None, rank: Optional[int] = None) -> Runtime:
             grp = dist.new_group(ranks) if plan.sp > 1 else None
             if g == plan.cfg_index:
                 sp_group = grp
-    return install(Runtime(plan, sp_group, None))
+    rt = Runtime(plan, sp_group, None)
+    if rt.p2p and plan.sp > 1:
+        rt.p2p = _probe_peer_memory(rt)
+    return install(rt)
+
+
+def _probe_peer_memory(rt: Runtime) -> bool:
+    """Collective: can every rank of every sequence-parallel group map its peers' memory (CUDA IPC + peer access)?  All
+    ranks get the same answer; on False the data path uses the NCCL all-to-all instead (same kernels, same results)."""
+    import torch
+    import torch.distributed as dist
+    ok = 1
+    try:
+        dev = torch.device("cuda", torch.cuda.current_device())
+        t, ptrs = rt.alloc_shared(256, dev)
+        t.fill_(1)
+        rt.ready()
+        ok = int(all(p for p in ptrs))
+    except Exception as e:   # noqa: BLE001 - any failure means "no peer memory here"
+        import warnings
+        warnings.warn(f"videopainter_b200: peer memory unavailable ({e}); using the NCCL all-to-all path")
+        ok = 0
+    flag = torch.tensor([ok], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    return bool(flag.item())
 
 
 def install(rt: Optional[Runtime]) -> Optional[Runtime]:
