@@ -25,7 +25,10 @@ namespace {
 constexpr int BQ = 128;          // query rows per softmax warpgroup
 constexpr int BKV = 128;         // keys per tile
 constexpr int DH = 64;           // head dim
-constexpr int KV_STAGES = 3;
+#ifndef VP_ATTN_KV_STAGES
+#define VP_ATTN_KV_STAGES 3
+#endif
+constexpr int KV_STAGES = VP_ATTN_KV_STAGES;
 constexpr int TILE_BYTES = BKV * DH * 2;   // 16 KiB (Q tile has the same size)
 constexpr int SMEM_Q = 0;
 constexpr int SMEM_K = 2 * TILE_BYTES;
@@ -48,6 +51,9 @@ constexpr float RESCALE_THRESHOLD = 8.0f;   // log2 units
 #ifndef VP_ATTN_POLY_PER16
 #define VP_ATTN_POLY_PER16 0                 // of every 8 element pairs, this many take the polynomial exp2 (0..8)
 #endif
+#ifndef VP_ATTN_FULLMAX
+#define VP_ATTN_FULLMAX 0                    // 1: every softmax warp also reads its partner's 64 columns for the row maximum
+#endif                                       //    (twice the TMEM read traffic, no shared-memory exchange / pair barrier)
 #ifndef VP_ATTN_LATE_ODONE
 #define VP_ATTN_LATE_ODONE 0                 // 1: wait for P_{j-1} V_{j-1} only before the first P store of tile j
 #endif
@@ -253,7 +259,34 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       uint32_t sr[64];
       tmem_ld_x32(tS + 0, sr + 0);
       tmem_ld_x32(tS + 32, sr + 32);
+#if VP_ATTN_FULLMAX
+      float omax;
+      {
+        const uint32_t tSo = tS + (half ? -64 : 64);             // the partner's columns of the same rows
+        int vo = BKV;                                            // how many of them are real keys
+        if (j == rag0) vo = val0 + half * 64 - (half ? 0 : 64);
+        else if (j == rag1) vo = val1 + half * 64 - (half ? 0 : 64);
+        uint32_t ot[32];
+        float m0 = -INFINITY, m1 = -INFINITY;
+        tmem_ld_x32(tSo, ot);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          m0 = max3(m0, i + 0 < vo ? __uint_as_float(ot[i + 0]) : -INFINITY, i + 1 < vo ? __uint_as_float(ot[i + 1]) : -INFINITY);
+          m1 = max3(m1, i + 2 < vo ? __uint_as_float(ot[i + 2]) : -INFINITY, i + 3 < vo ? __uint_as_float(ot[i + 3]) : -INFINITY);
+        }
+        tmem_ld_x32(tSo + 32, ot);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          m0 = max3(m0, i + 32 < vo ? __uint_as_float(ot[i + 0]) : -INFINITY, i + 33 < vo ? __uint_as_float(ot[i + 1]) : -INFINITY);
+          m1 = max3(m1, i + 34 < vo ? __uint_as_float(ot[i + 2]) : -INFINITY, i + 35 < vo ? __uint_as_float(ot[i + 3]) : -INFINITY);
+        }
+        omax = fmaxf(m0, m1);
+      }
+#else
       tmem_wait_ld();
+#endif
       tc_fence_before();
       mbar_arrive_a(a_s_free);                                // S_t may be overwritten by the next QKᵀ
 
@@ -277,6 +310,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       float tile_max = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
 #if defined(VP_ATTN_DEBUG_NOMAX)
       tile_max = 0.f;                                            // timing experiment only (wrong results)
+#elif VP_ATTN_FULLMAX
+      tile_max = fmaxf(tile_max, omax);
 #else
       // combine with the partner's half of the row (double-buffered by tile parity, one barrier per tile)
       sts_f32(a_xw + par * XBUF, tile_max);
