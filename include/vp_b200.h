@@ -118,7 +118,7 @@ int vp_attention_peer(const void* q, const void* k0, const void* v0, int kv_len0
                       float out_scale, void* stream);
 int vp_peer_barrier(void* const* peer_flags, int peers, int my_rank, unsigned int epoch, void* stream);
 /* Alternative to vp_attention_peer: chunk d (bytes_per_peer bytes) of the local buffer `src` is copied into slot my_rank of
- * rank d's buffer peer_dst[d] ([peers][bytes_per_peer]) by the copy engines, ordered in `stream`. */
+ * rank d's buffer peer_dst[d] ([peers][bytes_per_peer]) by one kernel of 16-byte peer stores (whole lines per warp). */
 int vp_peer_scatter(const void* src, void* const* peer_dst, int peers, int my_rank, long long bytes_per_peer, void* stream);
 /* Peer-visible device memory (host calls, synchronous): vp_peer_alloc = cudaMalloc + zero fill + CUDA IPC export (64-byte
  * handle, to be sent to the other ranks of the node by any means); vp_peer_open maps a peer's handle into the calling

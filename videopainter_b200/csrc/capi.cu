@@ -228,15 +228,10 @@ int vp_attention_peer(const void* q, const void* k0, const void* v0, int kv_len0
 int vp_peer_scatter(const void* src, void* const* peer_dst, int peers, int my_rank, long long bytes_per_peer, void* stream) {
   VP_REQUIRE(src && peer_dst && peers >= 1 && peers <= 8 && my_rank >= 0 && my_rank < peers && bytes_per_peer > 0, VP_ERR_BAD_SHAPE,
              "peer_scatter: bad arguments");
-  // chunk d of src goes to slot my_rank of rank d's buffer: `peers` contiguous device-to-device copies on the copy engines
-  // (NVLink for the remote ones), ordered in `stream`; starting with the next rank spreads the load over the links
-  for (int i = 0; i < peers; ++i) {
-    const int d = (my_rank + 1 + i) % peers;
-    VP_REQUIRE(peer_dst[d] != nullptr, VP_ERR_BAD_SHAPE, "peer_scatter: null peer pointer");
-    VP_CHECK_CUDA(cudaMemcpyAsync((char*)peer_dst[d] + (size_t)my_rank * bytes_per_peer, (const char*)src + (size_t)d * bytes_per_peer,
-                                  (size_t)bytes_per_peer, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
-  }
-  return VP_OK;
+  VP_REQUIRE(bytes_per_peer % 16 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0, VP_ERR_BAD_ALIGN,
+             "peer_scatter: 16-byte granularity");
+  for (int d = 0; d < peers; ++d) VP_REQUIRE(peer_dst[d] != nullptr, VP_ERR_BAD_SHAPE, "peer_scatter: null peer pointer");
+  return launch_peer_scatter(src, peer_dst, peers, my_rank, bytes_per_peer, (cudaStream_t)stream);
 }
 
 int vp_peer_alloc(long long bytes, void** ptr, unsigned char* handle64) {

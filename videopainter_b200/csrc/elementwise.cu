@@ -420,7 +420,33 @@ __global__ void peer_barrier_kernel(PeerFlags flags, int peers, int my_rank, uin
   __threadfence_system();
 }
 
+// Ulysses output exchange: chunk d of the local buffer -> slot my_rank of rank d's buffer; 16-byte vectors, every warp
+// writes 512 contiguous bytes (whole lines on the NVLink side).  One launch instead of `peers` copy-engine transfers, whose
+// fixed cost (~20 us each) dominates at these sizes.
+struct PeerPtrs { uint4* p[8]; };
+__global__ void __launch_bounds__(256) peer_scatter_kernel(const uint4* __restrict__ src, PeerPtrs dst, int peers, int my_rank,
+                                                           long long vec_per_peer) {
+  const long long total = vec_per_peer * peers;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int d = (int)(idx / vec_per_peer);
+    const long long off = idx - (long long)d * vec_per_peer;
+    dst.p[d][(long long)my_rank * vec_per_peer + off] = ldg_nc_v4(src + idx);
+  }
+}
+
 }  // namespace
+
+int launch_peer_scatter(const void* src, void* const* peer_dst, int peers, int my_rank, long long bytes_per_peer, cudaStream_t st) {
+  PeerPtrs d{};
+  for (int i = 0; i < peers; ++i) d.p[i] = (uint4*)peer_dst[i];
+  const long long vec = bytes_per_peer / 16;
+  long long blocks = (vec * peers + 255) / 256;
+  const int sms = sm_count();
+  if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
+  peer_scatter_kernel<<<(unsigned)blocks, 256, 0, st>>>((const uint4*)src, d, peers, my_rank, vec);
+  VP_CHECK_CUDA(cudaGetLastError());
+  return VP_OK;
+}
 
 int launch_peer_barrier(uint32_t* const* peer_flags, int peers, int my_rank, uint32_t epoch, cudaStream_t st) {
   PeerFlags f{};

@@ -356,7 +356,7 @@ def _block(pm: PackedModel, blk: PackedBlock, ws: _Workspace, x_in: torch.Tensor
             ws.peer_sync()                                            # every rank's q / k / v rows have landed
             if _PEER_ATTN_STORES:                                     # output rows stored by the kernel's own epilogue
                 ops.attention_peer(ws.q, ws.k, ws.v, ws.ptrs_ao, sh.sp_rank, ldo, Hl, S, S, scale, k1=k1, v1=v1, kv_len1=kv_len1)
-            else:                                                     # plain kernel + copy-engine scatter (measured faster)
+            else:                                                     # plain kernel + one scatter kernel of peer stores (measured faster)
                 ops.attention(ws.q, ws.k, ws.v, ws.ao, B, Hl, S, S, scale, k1=k1, v1=v1, kv_len1=kv_len1, ldo=ldo)
                 ws.rt.scatter(ws.ao, ws.ptrs_ao, R * ldo * 2)
             ws.peer_sync()                                            # every rank's output rows have landed in ao_recv
