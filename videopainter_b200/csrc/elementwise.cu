@@ -61,11 +61,27 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint
 // unit's first barrier, which every thread reaches only after its last read of `stat` in this unit.
 template <typename F>
 __device__ __forceinline__ void ln_block_stat(float (&v)[LN_RB], float* red, float* stat, int warp, int lane, int nwarps, F between) {
+  if (LN_RB == 4) {
+    // four rows reduced together in 6 shuffles instead of 20: lanes trade rows pairwise (16, 8), then fold (4, 2, 1);
+    // lanes [8r, 8r + 8) end up with the warp's sum of row r
+    const bool hi16 = lane & 16, hi8 = lane & 8;
+    float a0 = hi16 ? v[2] : v[0], a1 = hi16 ? v[3] : v[1];
+    const float s0 = hi16 ? v[0] : v[2], s1 = hi16 ? v[1] : v[3];
+    a0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+    a1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+    float k = hi8 ? a1 : a0;
+    k += __shfl_xor_sync(0xffffffffu, hi8 ? a0 : a1, 8);
+    k += __shfl_xor_sync(0xffffffffu, k, 4);
+    k += __shfl_xor_sync(0xffffffffu, k, 2);
+    k += __shfl_xor_sync(0xffffffffu, k, 1);
+    if ((lane & 7) == 0) red[(lane >> 3) * LN_MAX_WARPS + warp] = k;
+  } else {
 #pragma unroll
-  for (int r = 0; r < LN_RB; ++r) v[r] = warp_sum(v[r]);
-  if (lane == 0) {
+    for (int r = 0; r < LN_RB; ++r) v[r] = warp_sum(v[r]);
+    if (lane == 0) {
 #pragma unroll
-    for (int r = 0; r < LN_RB; ++r) red[r * LN_MAX_WARPS + warp] = v[r];
+      for (int r = 0; r < LN_RB; ++r) red[r * LN_MAX_WARPS + warp] = v[r];
+    }
   }
   __syncthreads();
   between();
@@ -93,39 +109,45 @@ __global__ void __launch_bounds__(WARPS * 32, LN_CTAS) ln_modulate_kernel(const 
   const float invD = 1.0f / (float)p.D;
   const uint32_t row_bytes = (uint32_t)p.D * 2u, stage_bytes = row_bytes * LN_RB;
 
-  // unit u -> (batch, expert, first row, row count)
-  auto unit = [&](int u, int& b, int& text, int& s0, int& n) {
-    b = u / units_per_batch;
-    const int k = u - b * units_per_batch;
+  // Each CTA walks a contiguous range of units; (batch, index within the batch) cursors advance without divisions.
+  const int u_begin = (int)((long long)blockIdx.x * total_units / gridDim.x);
+  const int u_end = (int)((long long)(blockIdx.x + 1) * total_units / gridDim.x);
+  auto rows_of = [&](int k, int& text, int& s0, int& n) {       // unit k of a batch -> expert, first row, row count
     text = k < units_text ? 1 : 0;
     s0 = text ? k * LN_RB : p.text_len + (k - units_text) * LN_RB;
     n = min(LN_RB, (text ? p.text_len : p.rows_per_batch) - s0);
   };
-  auto fetch = [&](int u, int stage) {                         // one thread: the unit's rows are contiguous in x
-    int b, text, s0, n;
-    unit(u, b, text, s0, n);
+  auto fetch = [&](int b, int k, int stage) {                   // one thread: the unit's rows are contiguous in x
+    int text, s0, n;
+    rows_of(k, text, s0, n);
     const __nv_bfloat16* x = p.x + ((long long)b * p.x_batch_rows + p.x_row_offset + s0) * p.D;
     mbar_arrive_expect_tx(&full[stage], (uint32_t)n * row_bytes);
     bulk_load(ln_smem + (size_t)stage * stage_bytes, x, (uint32_t)n * row_bytes, &full[stage]);
   };
 
+  int cb = u_begin / units_per_batch, ck = u_begin - cb * units_per_batch;        // cursor of the unit being processed
+  int fb = cb, fk = ck, fu = u_begin;                                              // cursor of the next unit to fetch
   if (threadIdx.x == 0) {
     for (int i = 0; i < stages; ++i) mbar_init(&full[i], 1);
     fence_barrier_init();
-    for (int i = 0; i < stages; ++i) {
-      const long long u = (long long)blockIdx.x + (long long)i * gridDim.x;
-      if (u < total_units) fetch((int)u, i);
-    }
   }
   __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < stages && fu < u_end; ++i, ++fu) {
+      fetch(fb, fk, i);
+      if (++fk == units_per_batch) { fk = 0; ++fb; }
+    }
+  }
 
   float A[8], C[8];
   int cur_b = -1, cur_text = -1;
   int stage = 0;
   uint32_t phase = 0;
-  for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
-    int b, text, s0, n;
-    unit(u, b, text, s0, n);
+  for (int u = u_begin; u < u_end; ++u) {
+    const int b = cb;
+    int text, s0, n;
+    rows_of(ck, text, s0, n);
+    if (++ck == units_per_batch) { ck = 0; ++cb; }
     if (active && (b != cur_b || text != cur_text)) {           // new (batch, expert): rebuild the coefficient registers
       cur_b = b; cur_text = text;
       float g[8], be[8];
@@ -147,7 +169,7 @@ __global__ void __launch_bounds__(WARPS * 32, LN_CTAS) ln_modulate_kernel(const 
     }
     __nv_bfloat16* y = p.y + ((long long)b * p.rows_per_batch + s0) * p.D + col;
 
-    mbar_wait(&full[stage], phase);
+    while (!mbar_try_wait(&full[stage], phase)) {}               // a bulk copy always completes: no watchdog needed here
     float v[LN_RB][8];                                             // unpacked once; three passes read them
     float st[LN_RB];
     const uint8_t* src = ln_smem + (size_t)stage * stage_bytes + (size_t)col * 2;
@@ -160,8 +182,11 @@ __global__ void __launch_bounds__(WARPS * 32, LN_CTAS) ln_modulate_kernel(const 
     }
     // after the first barrier of this reduction every thread holds its part of the stage in registers: refill the stage
     ln_block_stat(st, red[0], stat[0], warp, lane, nwarps, [&]() {
-      const long long un = (long long)u + (long long)stages * gridDim.x;
-      if (threadIdx.x == 0 && un < total_units) fetch((int)un, stage);
+      if (threadIdx.x == 0 && fu < u_end) {
+        fetch(fb, fk, stage);
+        ++fu;
+        if (++fk == units_per_batch) { fk = 0; ++fb; }
+      }
     });
 #pragma unroll
     for (int r = 0; r < LN_RB; ++r) {
