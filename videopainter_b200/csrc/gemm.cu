@@ -57,49 +57,6 @@ __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* p, const float* f) 
   }
 }
 
-// ---- plain / gelu / residual epilogue on 32 accumulator columns of one row -------------------------------------
-template <int EPI>
-__device__ __forceinline__ void epilogue_cols32(const GemmParams& p, const uint32_t* acc, int b, int s, int n0) {
-  float v[32];
-  if (p.bias) {
-    load_bf16x32(p.bias + n0, v);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(acc[j]);
-  } else {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-  }
-  if (EPI == EPI_BIAS) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
-  } else if (EPI == EPI_GELU) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
-  } else if (EPI == EPI_RESID) {
-    if (p.gate) {
-      const float* g = p.gate + (long long)b * p.gate_batch_stride + (s < p.text_len ? p.gate_text_off : p.gate_video_off) + n0;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float4 gv = __ldg(reinterpret_cast<const float4*>(g) + j);
-        v[j * 4 + 0] *= gv.x; v[j * 4 + 1] *= gv.y; v[j * 4 + 2] *= gv.z; v[j * 4 + 3] *= gv.w;
-      }
-    }
-    float r[32];
-    load_bf16x32(p.res + ((long long)b * p.res_batch_rows + p.res_row_offset + s) * p.ldr + n0, r);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] += r[j];
-    if (p.inject && s >= p.text_len) {
-      const int sv = s - p.text_len;
-      if (!p.inject_mask || p.inject_mask[(long long)b * p.video_len + sv] == 0) {
-        load_bf16x32(p.inject + (long long)b * p.inject_batch_stride + (long long)sv * p.ldi + n0, r);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += r[j];
-      }
-    }
-  }
-  store_bf16x32(p.out + ((long long)b * p.out_batch_rows + p.out_row_offset + s) * p.ldo + n0, v);
-}
-
 // ---- QKV epilogue on one head (64 accumulator columns) of one row ----------------------------------------------
 // Each thread owns one 128-byte output row (one head of one token).  Storing it directly would make every warp-wide
 // store touch 32 different lines with 16 bytes each — harmless behind the local L2, but over NVLink (peer mode) every
@@ -115,6 +72,23 @@ __device__ __forceinline__ void warp_store_rows128(uint8_t* stage, int lane, con
   for (int i = 0; i < 8; ++i) {
     const int r = i * 4 + (lane >> 3);
     const uint4 v = *reinterpret_cast<const uint4*>(stage + r * 128 + ((cc ^ (r & 7)) << 4));
+    const unsigned long long dr = __shfl_sync(0xffffffffu, d, r);
+    if (dr) *reinterpret_cast<uint4*>(dr + (cc << 4)) = v;
+  }
+  __syncwarp();
+}
+
+// The same for 64-byte row pieces (32 bf16 columns per thread): 4 lanes per row, 8 rows per store instruction.
+__device__ __forceinline__ void warp_store_rows64(uint8_t* stage, int lane, const uint4 (&c)[4], __nv_bfloat16* dst) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(stage + lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4)) = c[i];
+  __syncwarp();
+  const unsigned long long d = reinterpret_cast<unsigned long long>(dst);     // 0 = this row is not stored
+  const int cc = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = i * 8 + (lane >> 2);
+    const uint4 v = *reinterpret_cast<const uint4*>(stage + r * 64 + ((cc ^ ((r >> 1) & 3)) << 4));
     const unsigned long long dr = __shfl_sync(0xffffffffu, d, r);
     if (dr) *reinterpret_cast<uint4*>(dr + (cc << 4)) = v;
   }
@@ -222,6 +196,54 @@ __device__ __forceinline__ void epilogue_qkv_head(const GemmParams& p, const uin
       warp_store_rows128(stage, lane, out, row_ok ? p.k2_out + off : nullptr);
     }
   }
+}
+
+// ---- plain / gelu / residual epilogue on 32 accumulator columns of one row -------------------------------------
+// Runs warp-wide (row_ok = false lanes compute on zeros and store nothing); the 64-byte row pieces leave through the
+// swizzled shared-memory transpose so that every store instruction writes whole 64-byte row segments.
+template <int EPI>
+__device__ __forceinline__ void epilogue_cols32(const GemmParams& p, const uint32_t* acc, bool row_ok, int b, int s, int n0,
+                                                uint8_t* stage, int lane) {
+  float v[32];
+  if (p.bias) {
+    load_bf16x32(p.bias + n0, v);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(acc[j]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+  }
+  if (EPI == EPI_BIAS) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+  } else if (EPI == EPI_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
+  } else if (EPI == EPI_RESID && row_ok) {
+    if (p.gate) {
+      const float* g = p.gate + (long long)b * p.gate_batch_stride + (s < p.text_len ? p.gate_text_off : p.gate_video_off) + n0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 gv = __ldg(reinterpret_cast<const float4*>(g) + j);
+        v[j * 4 + 0] *= gv.x; v[j * 4 + 1] *= gv.y; v[j * 4 + 2] *= gv.z; v[j * 4 + 3] *= gv.w;
+      }
+    }
+    float r[32];
+    load_bf16x32(p.res + ((long long)b * p.res_batch_rows + p.res_row_offset + s) * p.ldr + n0, r);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] += r[j];
+    if (p.inject && s >= p.text_len) {
+      const int sv = s - p.text_len;
+      if (!p.inject_mask || p.inject_mask[(long long)b * p.video_len + sv] == 0) {
+        load_bf16x32(p.inject + (long long)b * p.inject_batch_stride + (long long)sv * p.ldi + n0, r);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += r[j];
+      }
+    }
+  }
+  uint4 u[4];
+  pack_bf16x32(v, u);
+  warp_store_rows64(stage, lane, u, row_ok ? p.out + ((long long)b * p.out_batch_rows + p.out_row_offset + s) * p.ldo + n0 : nullptr);
 }
 
 template <int EPI>
@@ -359,7 +381,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           uint32_t r[32];
           tmem_ld_x32(taddr + c * 32, r);
           tmem_wait_ld();
-          if (row_ok) epilogue_cols32<EPI>(p, r, b, s, n0);
+          epilogue_cols32<EPI>(p, r, row_ok, b, s, n0, smem + SMEM_EPI + (warp - 4) * EPI_STAGE_BYTES, lane);
         }
       }
       tc_fence_before();
