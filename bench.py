@@ -280,11 +280,22 @@ def main() -> None:
         breakdown[name] = {"launches": n, "ms_per_step": t / args.steps, "share": t / tot_ms if tot_ms else 0.0,
                            "avg_launch_ms": t / n, "tflops": (w / (t * 1e-3) / 1e12) if (w and name != "ln_modulate") else None,
                            "gbs": (w / (t * 1e-3) / 1e9) if name == "ln_modulate" else None}
+    # DRAM traffic of the dominant kernel per launch: from the committed ncu --set full capture (same shape, one launch)
+    traffic = None
+    try:
+        ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_attention_latest.json")))
+        to_bytes = lambda v: float(v.split()[0]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[v.split()[1]]   # noqa: E731
+        traffic = (to_bytes(ncu["dram__bytes_read.sum"]) + to_bytes(ncu["dram__bytes_write.sum"]))
+    except Exception:
+        traffic = None
     dom = max(prof.items(), key=lambda kv: kv[1][1])
     dn, (n_l, t_l, w_l) = dom
     achieved = w_l / (t_l * 1e-3) / 1e12
     roofline = {"kernel": dn, "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak_tf, "traffic": traffic if (dn == "attention" and world == 1) else None,
+                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one attention launch (B=2, 48 heads, S=17776) from "
+                                "profiles/ncu_attention_latest.json; algorithmic q+k+v+o bytes = 873.6 MB",
+                "peak_source": peak_src,
                 "flops_per_launch": w_l / n_l, "avg_launch_ms": t_l / n_l, "share_of_step": t_l / tot_ms}
     flops = step_flops(B_global, args.layers + BRANCH_LAYERS)
     out = {"metric": "denoise steps/s (49x480x720, CFG)", "value": 1000.0 / ms_per_step, "unit": "steps/s", "n_gpus": world,
