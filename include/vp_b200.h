@@ -89,7 +89,9 @@ int vp_gemm_gate_residual(const void* a, long long lda, const void* w, long long
  * w is [Wq; Wk; Wv] (qkv_first = 0) or [Wk; Wv] (qkv_first = 1, previous-window keys AP:2157-2172, 2247-2252).
  * row_scale[m] (nullable) multiplies the projection before the norm (prev_resample_mask * prev_clip_weight).
  * k2_out/v2_out (nullable) receive the masked copy of the ID-resample processor: K2 = RoPE(norm_k(k * mask2)),
- * V2 = v * mask2 (AP:2255-2281). rope tables are fp32 [video_len, 64] (nullable).
+ * V2 = v * mask2 (AP:2255-2281). rope tables are fp32 [video_len, 64] (nullable); rope_cs (nullable) is the compact form
+ * [video_len, 32][cos, sin] of tables that repeat every value twice, as get_1d_rotary_pos_embed builds them (EMB:641-642):
+ * when given it is used instead (one 256-byte fetch per token row and tile instead of 512 bytes per row and head).
  * heads_per_dest / dest_stride: head h of token s goes to
  *   x_out + (h / heads_per_dest) * dest_stride + ((b * heads_per_dest + h % heads_per_dest) * batch_rows + s) * 64,
  * i.e. heads_per_dest = heads (dest_stride ignored) is the plain [B, H, S, 64]; heads_per_dest = heads / P writes each
@@ -98,7 +100,7 @@ int vp_gemm_qkv(const void* a, long long lda, const void* w, long long ldw, cons
                 int heads, int qkv_first, void* q_out, void* k_out, void* v_out, void* k2_out, void* v2_out,
                 const uint8_t* mask2, const float* row_scale, const void* norm_q_w, const void* norm_q_b,
                 const void* norm_k_w, const void* norm_k_b, float qk_eps, const float* rope_cos, const float* rope_sin,
-                int text_len, int heads_per_dest, long long dest_stride, void* stream);
+                const float* rope_cs, int text_len, int heads_per_dest, long long dest_stride, void* stream);
 
 /* ---- Ulysses over NVLink peer memory: the all-to-all is fused into the producing kernels' epilogues ------------------
  * Every rank of the sequence-parallel group owns a q/k/v buffer [slot][heads/peers][seq_total][64] and an attention-output
@@ -111,8 +113,9 @@ int vp_gemm_qkv(const void* a, long long lda, const void* w, long long ldw, cons
 int vp_gemm_qkv_peer(const void* a, long long lda, const void* w, long long ldw, const void* bias, int m, int k, int heads,
                      int qkv_first, void* q_out, void* k_out, void* v_out, void* k2_out, void* v2_out, const uint8_t* mask2,
                      const float* row_scale, const void* norm_q_w, const void* norm_q_b, const void* norm_k_w,
-                     const void* norm_k_b, float qk_eps, const float* rope_cos, const float* rope_sin, int text_len,
-                     void* const* peer_base, int peers, const void* local_base, int seq_total, int row_offset, void* stream);
+                     const void* norm_k_b, float qk_eps, const float* rope_cos, const float* rope_sin, const float* rope_cs,
+                     int text_len, void* const* peer_base, int peers, const void* local_base, int seq_total, int row_offset,
+                     void* stream);
 int vp_attention_peer(const void* q, const void* k0, const void* v0, int kv_len0, const void* k1, const void* v1, int kv_len1,
                       void* const* peer_out, int peers, int my_rank, int ldo, int heads, int seq_q, float softmax_scale,
                       float out_scale, void* stream);

@@ -127,6 +127,18 @@ def test_gemm_qkv(ops, H, B, S, St):
     assert_close_bf16("qkv.v", v, y[2])
     assert_close_bf16("qkv.k2", k2, _ref_qk(y[1] * mk, *nk, cos, sin, St))
     assert_close_bf16("qkv.v2", v2, y[2] * mk)
+    # the compact (cos, sin)-pair table gives the same numbers as the general per-element tables
+    pairs = torch.stack([cos[:, 0::2], sin[:, 0::2]], dim=-1).reshape(Sv, 64).contiguous()
+    q3, k3, v3, k23, v23 = (torch.zeros(B, H, S, 64, dtype=BF16, device="cuda") for _ in range(5))
+    ops.gemm_qkv(a, w, bias, M, D, S, H, 0, q3, k3, v3, nq, nk, 1e-6, (cos, sin, pairs), St, k2_out=k23, v2_out=v23, mask2=mask2)
+    assert_close_bf16("qkv.q compact rope", q3, _ref_qk(y[0].clone(), *nq, cos, sin, St))
+    assert_close_bf16("qkv.k2 compact rope", k23, _ref_qk(y[1] * mk, *nk, cos, sin, St))
+    assert (q3.float() - q.float()).abs().max().item() <= 2 ** -6 and torch.equal(v3, v)
+    # a table that does NOT repeat its values pairwise must take the general path and still be exact
+    cos_g, sin_g = torch.rand(Sv, 64, device="cuda"), torch.rand(Sv, 64, device="cuda")
+    qg, kg, vg = (torch.zeros(B, H, S, 64, dtype=BF16, device="cuda") for _ in range(3))
+    ops.gemm_qkv(a, w, bias, M, D, S, H, 0, qg, kg, vg, nq, nk, 1e-6, (cos_g, sin_g), St)
+    assert_close_bf16("qkv.q general rope", qg, _ref_qk(y[0].clone(), *nq, cos_g, sin_g, St))
     # K/V-only projection of previous-window states with a per-row scale (AP:2247-2252)
     rs = torch.rand(M, device="cuda") * (torch.rand(M, device="cuda") > 0.3)
     pk, pv = (torch.zeros(B, H, S, 64, dtype=BF16, device="cuda") for _ in range(2))

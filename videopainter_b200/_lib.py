@@ -27,10 +27,10 @@ SIGNATURES = {
                               _i, _ll, _c_void_p],
     "vp_gemm_qkv": [_c_void_p, _ll, _c_void_p, _ll, _c_void_p, _i, _i, _i, _i, _i, _c_void_p, _c_void_p, _c_void_p,
                     _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _f,
-                    _c_void_p, _c_void_p, _i, _i, _ll, _c_void_p],
+                    _c_void_p, _c_void_p, _c_void_p, _i, _i, _ll, _c_void_p],
     "vp_gemm_qkv_peer": [_c_void_p, _ll, _c_void_p, _ll, _c_void_p, _i, _i, _i, _i, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                          _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _f, _c_void_p, _c_void_p,
-                         _i, _c_void_p, _i, _c_void_p, _i, _i, _c_void_p],
+                         _c_void_p, _i, _c_void_p, _i, _c_void_p, _i, _i, _c_void_p],
     "vp_attention_peer": [_c_void_p, _c_void_p, _c_void_p, _i, _c_void_p, _c_void_p, _i, _c_void_p, _i, _i, _i, _i, _i, _f, _f,
                           _c_void_p],
     "vp_peer_barrier": [_c_void_p, _i, _i, C.c_uint, _c_void_p],

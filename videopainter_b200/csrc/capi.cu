@@ -134,7 +134,8 @@ static int gemm_qkv_impl(const void* a, long long lda, const void* w, long long 
                          int heads, int qkv_first, void* q_out, void* k_out, void* v_out, void* k2_out, void* v2_out,
                          const uint8_t* mask2, const float* row_scale, const void* norm_q_w, const void* norm_q_b,
                          const void* norm_k_w, const void* norm_k_b, float qk_eps, const float* rope_cos, const float* rope_sin,
-                         int text_len, int heads_per_dest, long long dest_stride, const PeerDest& peer, void* stream) {
+                         const float* rope_cs, int text_len, int heads_per_dest, long long dest_stride, const PeerDest& peer,
+                         void* stream) {
   VP_REQUIRE(a && w && bias && k_out && v_out && norm_k_w && norm_k_b, VP_ERR_BAD_SHAPE, "gemm_qkv: null pointer");
   VP_REQUIRE(heads_per_dest > 0 && heads % heads_per_dest == 0 && dest_stride % 8 == 0, VP_ERR_BAD_SHAPE,
              "gemm_qkv: heads_per_dest must divide heads");
@@ -154,7 +155,7 @@ static int gemm_qkv_impl(const void* a, long long lda, const void* w, long long 
   p.nq_w = (const __nv_bfloat16*)norm_q_w; p.nq_b = (const __nv_bfloat16*)norm_q_b;
   p.nk_w = (const __nv_bfloat16*)norm_k_w; p.nk_b = (const __nv_bfloat16*)norm_k_b;
   p.qk_eps = qk_eps;
-  p.rope_cos = rope_cos; p.rope_sin = rope_sin;
+  p.rope_cos = rope_cos; p.rope_sin = rope_sin; p.rope_cs = rope_cs;
   p.text_len = text_len;
   p.heads_per_dest = heads_per_dest; p.dest_stride = dest_stride;
   if (peer.base) {
@@ -174,22 +175,24 @@ int vp_gemm_qkv(const void* a, long long lda, const void* w, long long ldw, cons
                 int heads, int qkv_first, void* q_out, void* k_out, void* v_out, void* k2_out, void* v2_out,
                 const uint8_t* mask2, const float* row_scale, const void* norm_q_w, const void* norm_q_b,
                 const void* norm_k_w, const void* norm_k_b, float qk_eps, const float* rope_cos, const float* rope_sin,
-                int text_len, int heads_per_dest, long long dest_stride, void* stream) {
+                const float* rope_cs, int text_len, int heads_per_dest, long long dest_stride, void* stream) {
   return gemm_qkv_impl(a, lda, w, ldw, bias, m, k, batch_rows, heads, qkv_first, q_out, k_out, v_out, k2_out, v2_out, mask2,
-                       row_scale, norm_q_w, norm_q_b, norm_k_w, norm_k_b, qk_eps, rope_cos, rope_sin, text_len, heads_per_dest,
-                       dest_stride, PeerDest{}, stream);
+                       row_scale, norm_q_w, norm_q_b, norm_k_w, norm_k_b, qk_eps, rope_cos, rope_sin, rope_cs, text_len,
+                       heads_per_dest, dest_stride, PeerDest{}, stream);
 }
 
 int vp_gemm_qkv_peer(const void* a, long long lda, const void* w, long long ldw, const void* bias, int m, int k, int heads,
                      int qkv_first, void* q_out, void* k_out, void* v_out, void* k2_out, void* v2_out, const uint8_t* mask2,
                      const float* row_scale, const void* norm_q_w, const void* norm_q_b, const void* norm_k_w,
-                     const void* norm_k_b, float qk_eps, const float* rope_cos, const float* rope_sin, int text_len,
-                     void* const* peer_base, int peers, const void* local_base, int seq_total, int row_offset, void* stream) {
+                     const void* norm_k_b, float qk_eps, const float* rope_cos, const float* rope_sin, const float* rope_cs,
+                     int text_len, void* const* peer_base, int peers, const void* local_base, int seq_total, int row_offset,
+                     void* stream) {
   VP_REQUIRE(peer_base && peers >= 1 && heads % peers == 0, VP_ERR_BAD_SHAPE, "gemm_qkv_peer: peers must divide heads");
   PeerDest pd;
   pd.base = peer_base; pd.peers = peers; pd.local_base = local_base; pd.seq = seq_total; pd.row_off = row_offset;
   return gemm_qkv_impl(a, lda, w, ldw, bias, m, k, m, heads, qkv_first, q_out, k_out, v_out, k2_out, v2_out, mask2, row_scale,
-                       norm_q_w, norm_q_b, norm_k_w, norm_k_b, qk_eps, rope_cos, rope_sin, text_len, heads / peers, 0, pd, stream);
+                       norm_q_w, norm_q_b, norm_k_w, norm_k_b, qk_eps, rope_cos, rope_sin, rope_cs, text_len, heads / peers, 0, pd,
+                       stream);
 }
 
 int vp_attention(const void* q, const void* k0, const void* v0, int kv_len0, const void* k1, const void* v1, int kv_len1,

@@ -105,47 +105,75 @@ __device__ __forceinline__ void pack_bf16x32(const float* f, uint4* u) {
   }
 }
 
-// LayerNorm(64) of (x * pre) with affine (w, bia), optional interleaved-pair RoPE, packed to bf16 in `out` (8 x 16 bytes)
-__device__ __forceinline__ void ln64_rope_pack(const float* x, float pre, const __nv_bfloat16* w, const __nv_bfloat16* bia,
-                                               float eps, const float* cosr, const float* sinr, uint4 (&out)[8]) {
-  float mean = 0.f;
+__device__ __forceinline__ void load_bf16x16(const __nv_bfloat16* p, float* f) {
 #pragma unroll
-  for (int j = 0; j < 64; ++j) mean += x[j];
-  mean *= pre * (1.0f / 64.0f);
-  float var = 0.f;
-#pragma unroll
-  for (int j = 0; j < 64; ++j) {
-    float d = x[j] * pre - mean;
-    var += d * d;
+  for (int i = 0; i < 2; ++i) {
+    uint4 u = __ldg(reinterpret_cast<const uint4*>(p) + i);
+    f[i * 8 + 0] = bf16_lo(u.x); f[i * 8 + 1] = bf16_hi(u.x);
+    f[i * 8 + 2] = bf16_lo(u.y); f[i * 8 + 3] = bf16_hi(u.y);
+    f[i * 8 + 4] = bf16_lo(u.z); f[i * 8 + 5] = bf16_hi(u.z);
+    f[i * 8 + 6] = bf16_lo(u.w); f[i * 8 + 7] = bf16_hi(u.w);
   }
-  const float rstd = rsqrtf(var * (1.0f / 64.0f) + eps);
+}
+
+// LayerNorm(64) of (x * pre) with affine (w, bia), optional interleaved-pair RoPE, packed to bf16 in `out` (8 x 16 bytes).
+// RoPE (EMB:683-692: out = x*cos + rot(x)*sin, rot(x)[2i] = -x[2i+1], rot(x)[2i+1] = x[2i]) comes either from `cs` — this
+// row's 32 (cos, sin) pairs, already in registers, valid when the tables repeat every value twice as the reference builds
+// them (EMB:641-642) — or from the general per-element tables cosr / sinr.
+__device__ __forceinline__ void ln64_rope_pack(const float* x, float pre, const __nv_bfloat16* w, const __nv_bfloat16* bia,
+                                               float eps, const float* cs, const float* cosr, const float* sinr, uint4 (&out)[8]) {
+  float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;             // four partial sums: no 64-long dependency chain
 #pragma unroll
-  for (int c = 0; c < 2; ++c) {   // 32 columns at a time keeps the live set small
-    float g[32], be[32], y[32];
-    load_bf16x32(w + c * 32, g);
-    load_bf16x32(bia + c * 32, be);
+  for (int j = 0; j < 64; j += 4) { m0 += x[j]; m1 += x[j + 1]; m2 += x[j + 2]; m3 += x[j + 3]; }
+  const float mean = ((m0 + m1) + (m2 + m3)) * pre * (1.0f / 64.0f);
+  float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) y[j] = (x[c * 32 + j] * pre - mean) * rstd * g[j] + be[j];
-    if (cosr) {
+  for (int j = 0; j < 64; j += 4) {
+    const float d0 = fmaf(x[j], pre, -mean), d1 = fmaf(x[j + 1], pre, -mean), d2 = fmaf(x[j + 2], pre, -mean), d3 = fmaf(x[j + 3], pre, -mean);
+    v0 = fmaf(d0, d0, v0); v1 = fmaf(d1, d1, v1); v2 = fmaf(d2, d2, v2); v3 = fmaf(d3, d3, v3);
+  }
+  const float rstd = rsqrtf(((v0 + v1) + (v2 + v3)) * (1.0f / 64.0f) + eps);
+  const float a = pre * rstd, nb = -mean * rstd;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {   // 16 columns at a time keeps the live set small
+    float g[16], be[16], y[16];
+    load_bf16x16(w + c * 16, g);
+    load_bf16x16(bia + c * 16, be);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) y[j] = fmaf(fmaf(x[c * 16 + j], a, nb), g[j], be[j]);
+    if (cs) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float4 cv = __ldg(reinterpret_cast<const float4*>(cosr + c * 32) + j);
-        float4 sv = __ldg(reinterpret_cast<const float4*>(sinr + c * 32) + j);
+        const float co = cs[(c * 8 + j) * 2], si = cs[(c * 8 + j) * 2 + 1];
+        const float a0 = y[2 * j], a1 = y[2 * j + 1];
+        y[2 * j] = fmaf(a0, co, -a1 * si);
+        y[2 * j + 1] = fmaf(a1, co, a0 * si);
+      }
+    } else if (cosr) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float4 cv = __ldg(reinterpret_cast<const float4*>(cosr + c * 16) + j);
+        float4 sv = __ldg(reinterpret_cast<const float4*>(sinr + c * 16) + j);
         const float a0 = y[j * 4 + 0], a1 = y[j * 4 + 1], a2 = y[j * 4 + 2], a3 = y[j * 4 + 3];
-        // EMB:683-692: out = x*cos + rot(x)*sin, rot(x)[2i] = -x[2i+1], rot(x)[2i+1] = x[2i]
         y[j * 4 + 0] = a0 * cv.x - a1 * sv.x;
         y[j * 4 + 1] = a1 * cv.y + a0 * sv.y;
         y[j * 4 + 2] = a2 * cv.z - a3 * sv.z;
         y[j * 4 + 3] = a3 * cv.w + a2 * sv.w;
       }
     }
-    pack_bf16x32(y, &out[c * 4]);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      out[c * 2 + i].x = pack_bf16(y[i * 8 + 0], y[i * 8 + 1]);
+      out[c * 2 + i].y = pack_bf16(y[i * 8 + 2], y[i * 8 + 3]);
+      out[c * 2 + i].z = pack_bf16(y[i * 8 + 4], y[i * 8 + 5]);
+      out[c * 2 + i].w = pack_bf16(y[i * 8 + 6], y[i * 8 + 7]);
+    }
   }
 }
 
 // Runs warp-wide (all 32 lanes, also those whose row is out of range: row_ok = false stores nothing).
 __device__ __forceinline__ void epilogue_qkv_head(const GemmParams& p, const uint32_t* acc, bool row_ok, int m, int b, int s, int n0,
-                                                  uint8_t* stage, int lane) {
+                                                  uint8_t* stage, int lane, const float* cs) {
   float x[64];
   load_bf16x32(p.bias + n0, x);
   load_bf16x32(p.bias + n0 + 32, x + 32);
@@ -181,18 +209,18 @@ __device__ __forceinline__ void epilogue_qkv_head(const GemmParams& p, const uin
     }
     return;
   }
-  const bool rope = p.rope_cos != nullptr && s >= p.text_len && row_ok;
+  const bool rope = cs == nullptr && p.rope_cos != nullptr && s >= p.text_len && row_ok;
   const float* cosr = rope ? p.rope_cos + (long long)(s - p.text_len) * 64 : nullptr;
   const float* sinr = rope ? p.rope_sin + (long long)(s - p.text_len) * 64 : nullptr;
   if (which == 0) {
-    ln64_rope_pack(x, rs, p.nq_w, p.nq_b, p.qk_eps, cosr, sinr, out);
+    ln64_rope_pack(x, rs, p.nq_w, p.nq_b, p.qk_eps, cs, cosr, sinr, out);
     warp_store_rows128(stage, lane, out, row_ok ? p.q_out + off : nullptr);
   } else {
-    ln64_rope_pack(x, rs, p.nk_w, p.nk_b, p.qk_eps, cosr, sinr, out);
+    ln64_rope_pack(x, rs, p.nk_w, p.nk_b, p.qk_eps, cs, cosr, sinr, out);
     warp_store_rows128(stage, lane, out, row_ok ? p.k_out + off : nullptr);
     if (p.k2_out) {
       const float mk = (row_ok && p.mask2[m]) ? 1.0f : 0.0f;    // masked-out keys become RoPE(norm_k.bias): AP:2255, 2272, 2281
-      ln64_rope_pack(x, mk, p.nk_w, p.nk_b, p.qk_eps, cosr, sinr, out);
+      ln64_rope_pack(x, mk, p.nk_w, p.nk_b, p.qk_eps, cs, cosr, sinr, out);
       warp_store_rows128(stage, lane, out, row_ok ? p.k2_out + off : nullptr);
     }
   }
@@ -363,6 +391,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(quad * 32) << 16);
       if (EPI == EPI_QKV) {
+        // the four heads of this tile share the token row: its RoPE pairs are fetched once (compact table, 256 B per row)
+        float cs[64];
+        const bool use_cs = p.rope_cs != nullptr && (n_blk * BN) / p.d_model + p.qkv_first != 2 && row_ok && s >= p.text_len;
+        if (use_cs) {
+          const float4* src = reinterpret_cast<const float4*>(p.rope_cs + (long long)(s - p.text_len) * 64);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float4 t4 = __ldg(src + i);
+            cs[i * 4 + 0] = t4.x; cs[i * 4 + 1] = t4.y; cs[i * 4 + 2] = t4.z; cs[i * 4 + 3] = t4.w;
+          }
+        }
 #pragma unroll 1
         for (int hc = 0; hc < BN / 64; ++hc) {
           const int n0 = n_blk * BN + hc * 64;
@@ -371,7 +410,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           tmem_ld_x32(taddr + hc * 64, r);
           tmem_ld_x32(taddr + hc * 64 + 32, r + 32);
           tmem_wait_ld();
-          epilogue_qkv_head(p, r, row_ok, m, b, s, n0, smem + SMEM_EPI + (warp - 4) * EPI_STAGE_BYTES, lane);
+          epilogue_qkv_head(p, r, row_ok, m, b, s, n0, smem + SMEM_EPI + (warp - 4) * EPI_STAGE_BYTES, lane, use_cs ? cs : nullptr);
         }
       } else {
 #pragma unroll 1

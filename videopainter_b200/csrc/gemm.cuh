@@ -70,6 +70,7 @@ struct GemmParams {
   float qk_eps;
   const float* rope_cos;          // [Sv, 64] fp32 or null
   const float* rope_sin;
+  const float* rope_cs;           // [Sv, 32][cos, sin] fp32: compact form of pair-repeated tables (preferred when given)
 };
 
 int launch_gemm(int epi, const void* A, long long lda, const void* W, long long ldw, const GemmParams& p, cudaStream_t st);

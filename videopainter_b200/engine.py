@@ -410,19 +410,34 @@ def _block(pm: PackedModel, blk: PackedBlock, ws: _Workspace, x_in: torch.Tensor
                            gate_text_off=5 * D, text_len=St, **inj_kw)
 
 
+_rope_cache: Dict[Any, Any] = {}
+
+
 def _prep_rope(rope, device, Sv, sh: Optional[Shard] = None):
-    """(cos, sin) fp32 [Sv, 64] on the device; for a shard, the rows of its own video tokens (row s - text_rows of the
-    returned tables belongs to owned row s)."""
+    """(cos, sin, pairs) on the device: cos / sin fp32 [Sv, 64] as given, pairs = compact [Sv, 32, (cos, sin)] when the
+    tables repeat every value twice (the reference's construction, EMB:641-642) else None.  For a shard, the rows of its
+    own video tokens (row s - text_rows of the returned tables belongs to owned row s).  The pair check costs one device
+    synchronisation, so the result is cached per input tensor (the pipeline builds the tables once per window: PIPE:922)."""
     if rope is None:
         return None
-    cos, sin = rope
-    cos = cos.to(device=device, dtype=torch.float32).contiguous()
-    sin = sin.to(device=device, dtype=torch.float32).contiguous()
-    if cos.shape != (Sv, 64) or sin.shape != (Sv, 64):
-        raise ValueError(f"image_rotary_emb must be two [{Sv}, 64] tables, got {tuple(cos.shape)}")
+    key = (rope[0].data_ptr(), rope[0]._version, rope[1].data_ptr(), rope[1]._version, str(device), Sv)
+    hit = _rope_cache.get(key)
+    if hit is None:
+        cos = rope[0].to(device=device, dtype=torch.float32).contiguous()
+        sin = rope[1].to(device=device, dtype=torch.float32).contiguous()
+        if cos.shape != (Sv, 64) or sin.shape != (Sv, 64):
+            raise ValueError(f"image_rotary_emb must be two [{Sv}, 64] tables, got {tuple(cos.shape)}")
+        pairs = None
+        if torch.equal(cos[:, 0::2], cos[:, 1::2]) and torch.equal(sin[:, 0::2], sin[:, 1::2]):
+            pairs = torch.stack([cos[:, 0::2], sin[:, 0::2]], dim=-1).reshape(Sv, 64).contiguous()
+        if len(_rope_cache) > 8:
+            _rope_cache.clear()
+        hit = _rope_cache[key] = (cos, sin, pairs, rope)      # keep the inputs alive: the key holds their addresses
+    cos, sin, pairs = hit[:3]
     if sh is not None and sh.sp > 1:
         cos, sin = cos[sh.video0:], sin[sh.video0:]
-    return cos, sin
+        pairs = None if pairs is None else pairs[sh.video0:]
+    return cos, sin, pairs
 
 
 def _check_inputs(pm: PackedModel, hidden_states, encoder_hidden_states):

@@ -159,14 +159,23 @@ def gemm_qkv(a, w, bias, m, k, batch_rows, heads, qkv_first, q_out, k_out, v_out
              k2_out=None, v2_out=None, mask2=None, row_scale=None, ldw=None, heads_per_dest=None, dest_stride=0):
     """heads_per_dest / dest_stride: Ulysses send layout (include/vp_b200.h); q_out .. v2_out may then be views into one send
     buffer, so only their base addresses are taken."""
-    cos, sin = (None, None) if rope is None else rope
+    cos, sin, cs = _rope3(rope)
     check(lib().vp_gemm_qkv(
         _p(a, BF16, "qkv.a"), k, _p(w, BF16, "qkv.w") if w.is_contiguous() else w.data_ptr(), ldw or k, _p(bias, BF16, "qkv.bias"),
         m, k, batch_rows, heads, qkv_first, _base(q_out), _base(k_out), _base(v_out), _base(k2_out), _base(v2_out),
         _p(mask2, torch.uint8, "qkv.mask2"), _p(row_scale, torch.float32, "qkv.row_scale"),
         _p(norm_q[0], BF16) if norm_q else None, _p(norm_q[1], BF16) if norm_q else None, _p(norm_k[0], BF16), _p(norm_k[1], BF16),
-        float(qk_eps), _base(cos, torch.float32), _base(sin, torch.float32), text_len, heads_per_dest or heads, dest_stride,
-        _stream()), "vp_gemm_qkv")
+        float(qk_eps), _base(cos, torch.float32), _base(sin, torch.float32), _base(cs, torch.float32), text_len,
+        heads_per_dest or heads, dest_stride, _stream()), "vp_gemm_qkv")
+
+
+def _rope3(rope):
+    """rope = None | (cos, sin) | (cos, sin, compact [Sv, 32, 2] pairs or None)"""
+    if rope is None:
+        return None, None, None
+    if len(rope) == 2:
+        return rope[0], rope[1], None
+    return rope
 
 
 def _ptr_array(ptrs):
@@ -179,13 +188,14 @@ def gemm_qkv_peer(a, w, bias, m, k, heads, qkv_first, q_out, k_out, v_out, norm_
                   local_base, seq_total, row_offset, k2_out=None, v2_out=None, mask2=None, row_scale=None, ldw=None):
     """QKV GEMM whose epilogue stores each head into its destination rank's attention buffer over peer memory
     (include/vp_b200.h vp_gemm_qkv_peer).  peer_ptrs: data pointers of every rank's buffer, by rank."""
-    cos, sin = (None, None) if rope is None else rope
+    cos, sin, cs = _rope3(rope)
     check(lib().vp_gemm_qkv_peer(
         _p(a, BF16, "qkv.a"), k, _p(w, BF16, "qkv.w") if w.is_contiguous() else w.data_ptr(), ldw or k, _p(bias, BF16, "qkv.bias"),
         m, k, heads, qkv_first, _base(q_out), _base(k_out), _base(v_out), _base(k2_out), _base(v2_out),
         _p(mask2, torch.uint8, "qkv.mask2"), _p(row_scale, torch.float32, "qkv.row_scale"),
         _p(norm_q[0], BF16) if norm_q else None, _p(norm_q[1], BF16) if norm_q else None, _p(norm_k[0], BF16), _p(norm_k[1], BF16),
-        float(qk_eps), _base(cos, torch.float32), _base(sin, torch.float32), text_len, _ptr_array(peer_ptrs), len(peer_ptrs),
+        float(qk_eps), _base(cos, torch.float32), _base(sin, torch.float32), _base(cs, torch.float32), text_len,
+        _ptr_array(peer_ptrs), len(peer_ptrs),
         _base(local_base), seq_total, row_offset, _stream()), "vp_gemm_qkv_peer")
 
 
