@@ -47,23 +47,32 @@ constexpr int SOFTMAX_REGS = VP_ATTN_SOFTMAX_REGS, OTHER_REGS = VP_ATTN_OTHER_RE
 static_assert(512 * SOFTMAX_REGS + 128 * OTHER_REGS <= 640 * 96, "register pool of the CTA exceeded");
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t COL_S = 0, COL_P = 128, COL_O = 192, COL_TILE = 256;
-constexpr float RESCALE_THRESHOLD = 8.0f;   // log2 units
 #ifndef VP_ATTN_POLY_PER16
 #define VP_ATTN_POLY_PER16 0                 // of every 8 element pairs, this many take the polynomial exp2 (0..8)
+#endif
+#ifndef VP_ATTN_LEAN_WAIT
+#define VP_ATTN_LEAN_WAIT 0                  // 1: softmax warps spin on try_wait without the watchdog (smaller loop body)
+#endif
+#ifndef VP_ATTN_UNROLL2
+#define VP_ATTN_UNROLL2 1                    // 1: key-tile loop unrolled by two (barrier parities become constants)
 #endif
 #ifndef VP_ATTN_FULLMAX
 #define VP_ATTN_FULLMAX 0                    // 1: every softmax warp also reads its partner's 64 columns for the row maximum
 #endif                                       //    (twice the TMEM read traffic, no shared-memory exchange / pair barrier)
+#ifndef VP_ATTN_RESCALE_LOG2
+#define VP_ATTN_RESCALE_LOG2 8.0f
+#endif
+constexpr float RESCALE_THRESHOLD = VP_ATTN_RESCALE_LOG2;   // log2 units
 #ifndef VP_ATTN_LATE_ODONE
 #define VP_ATTN_LATE_ODONE 0                 // 1: wait for P_{j-1} V_{j-1} only before the first P store of tile j
 #endif
 #ifndef VP_ATTN_SKEW_CLK
 #define VP_ATTN_SKEW_CLK 0                   // query tile 1 starts its softmax this many clocks late (de-phases the two tiles)
 #endif
-#ifndef VP_ATTN_POLY_CHUNKS_EVEN
-#define VP_ATTN_POLY_CHUNKS_EVEN 0           // bit ch set: 16-column chunk ch of an even key tile takes the polynomial exp2
-#define VP_ATTN_POLY_CHUNKS_ODD 0            // the same for odd key tiles (finer control of the MUFU / FMA balance)
+#ifndef VP_ATTN_CHUNK_PAIRS
+#define VP_ATTN_CHUNK_PAIRS 8                // element pairs per P hand-off chunk (4, 8 or 16: tcgen05.st x4 / x8 / x16)
 #endif
+// (whole chunks on a four-pairs-at-a-time staged polynomial were measured too: slower than none at every share)
 // (ex2.approx.ftz.bf16x2 was measured too: it lowers to two MUFU.EX2.BF16 operations, 16 clk per pair — no gain.)
 
 
@@ -122,43 +131,12 @@ __device__ __forceinline__ void exp2_poly2(uint64_t y2, float& e0, float& e1) {
   e1 = __uint_as_float(__float_as_uint(pb) + (__float_as_uint(tb) << 23));
 }
 
-// The same for four pairs at once, stage by stage: consecutive instructions are independent, so the in-order warp never
-// waits on the 4-5 clk FFMA2 latency of its own chain.
-__device__ __forceinline__ void exp2_poly2x4(const uint64_t* y2in, float* e) {
-  const uint64_t magic = pack2(12582912.0f, 12582912.0f);
-  const uint64_t nmagic = pack2(-12582912.0f, -12582912.0f);
-  const uint64_t one = pack2(1.0f, 1.0f), mone = pack2(-1.0f, -1.0f);
-  const uint64_t c3 = pack2(0.055171459913253784f, 0.055171459913253784f);
-  const uint64_t c2 = pack2(0.2426108568906784f, 0.2426108568906784f);
-  const uint64_t c1 = pack2(0.6932609677314758f, 0.6932609677314758f);
-  const uint64_t c0 = pack2(0.9999281167984009f, 0.9999281167984009f);
-  uint64_t y2[4], t2[4], f2[4], p2[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float ya, yb;
-    unpack2(y2in[i], ya, yb);
-    y2[i] = pack2(fmaxf(ya, -126.0f), fmaxf(yb, -126.0f));
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) t2[i] = fma2(y2[i], one, magic);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) f2[i] = fma2(t2[i], one, nmagic);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) f2[i] = fma2(f2[i], mone, y2[i]);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) p2[i] = fma2(f2[i], c3, c2);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) p2[i] = fma2(p2[i], f2[i], c1);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) p2[i] = fma2(p2[i], f2[i], c0);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float ta, tb, pa, pb;
-    unpack2(t2[i], ta, tb);
-    unpack2(p2[i], pa, pb);
-    e[2 * i] = __uint_as_float(__float_as_uint(pa) + (__float_as_uint(ta) << 23));
-    e[2 * i + 1] = __uint_as_float(__float_as_uint(pb) + (__float_as_uint(tb) << 23));
-  }
+__device__ __forceinline__ void softmax_wait(uint32_t bar, uint32_t parity) {
+#if VP_ATTN_LEAN_WAIT
+  while (!mbar_try_wait_a(bar, parity)) {}
+#else
+  mbar_wait_a(bar, parity);
+#endif
 }
 
 struct Bars {
@@ -252,9 +230,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       const long long t0 = clock64();
       while (clock64() - t0 < VP_ATTN_SKEW_CLK) {}
     }
+#if VP_ATTN_UNROLL2
+#pragma unroll 2
+#endif
     for (int j = 0; j < n_tiles; ++j) {
       const uint32_t par = j & 1;
-      mbar_wait_a(a_s_full, par);
+      softmax_wait(a_s_full, par);
       tc_fence_after();
       uint32_t sr[64];
       tmem_ld_x32(tS + 0, sr + 0);
@@ -327,7 +308,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         m_used = m_new;
         row_sum *= factor;
         if (j > 0) {
-          mbar_wait_a(a_o_done, (j - 1) & 1);                          // P_{j-1} V_{j-1} finished
+          softmax_wait(a_o_done, (j - 1) & 1);                          // P_{j-1} V_{j-1} finished
           tc_fence_after();
           waited_o = true;
           uint32_t o[32];                                              // this warp rescales its 32 columns of O
@@ -340,7 +321,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
 #if !VP_ATTN_LATE_ODONE
       if (j > 0 && !waited_o) {                                        // P region still read by P_{j-1} V_{j-1}
-        mbar_wait_a(a_o_done, (j - 1) & 1);
+        softmax_wait(a_o_done, (j - 1) & 1);
         tc_fence_after();
       }
 #endif
@@ -349,52 +330,40 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       uint64_t acc0 = pack2(0.f, 0.f), acc1 = pack2(0.f, 0.f);
       // 16 columns at a time: scale, exponentiate, accumulate the row sum, pack to bf16 and hand the 8 packed words to
       // TMEM right away (few live registers, and the MUFU / FMA / ALU work of neighbouring chunks overlaps)
-      const uint32_t poly_mask = (j & 1) ? VP_ATTN_POLY_CHUNKS_ODD : VP_ATTN_POLY_CHUNKS_EVEN;
+      constexpr int CP = VP_ATTN_CHUNK_PAIRS;                       // pairs per chunk
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        uint32_t pk[8];
-        uint64_t y2[8];
+      for (int ch = 0; ch < 32 / CP; ++ch) {
+        uint32_t pk[CP];
+        uint64_t y2[CP];
 #pragma unroll
-        for (int pr = 0; pr < 8; ++pr)
-          y2[pr] = fma2(pack2(__uint_as_float(sr[ch * 16 + 2 * pr]), __uint_as_float(sr[ch * 16 + 2 * pr + 1])), c2v, nmc2);
-        if (((VP_ATTN_POLY_CHUNKS_EVEN | VP_ATTN_POLY_CHUNKS_ODD) >> ch) & 1 && (poly_mask >> ch) & 1) {
+        for (int pr = 0; pr < CP; ++pr)
+          y2[pr] = fma2(pack2(__uint_as_float(sr[(ch * CP + pr) * 2]), __uint_as_float(sr[(ch * CP + pr) * 2 + 1])), c2v, nmc2);
 #pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            float e[8];
-            exp2_poly2x4(y2 + 4 * g, e);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              pk[4 * g + i] = pack_bf16(e[2 * i], e[2 * i + 1]);
-              if (i & 1) acc1 = fma2(pack2(e[2 * i], e[2 * i + 1]), one2, acc1);
-              else acc0 = fma2(pack2(e[2 * i], e[2 * i + 1]), one2, acc0);
-            }
-          }
-        } else {
-#pragma unroll
-          for (int pr = 0; pr < 8; ++pr) {
-            float e0, e1;
-            if (pr < VP_ATTN_POLY_PER16) {
-              exp2_poly2(y2[pr], e0, e1);
-            } else {
-              float y0, y1;
-              unpack2(y2[pr], y0, y1);
+        for (int pr = 0; pr < CP; ++pr) {
+          float e0, e1;
+          if ((pr & 7) < VP_ATTN_POLY_PER16) {
+            exp2_poly2(y2[pr], e0, e1);
+          } else {
+            float y0, y1;
+            unpack2(y2[pr], y0, y1);
 #if defined(VP_ATTN_DEBUG_NOEXP)
-              e0 = y0; e1 = y1;                                    // timing experiment only (wrong results)
+            e0 = y0; e1 = y1;                                      // timing experiment only (wrong results)
 #else
-              e0 = fast_exp2(y0);
-              e1 = fast_exp2(y1);
+            e0 = fast_exp2(y0);
+            e1 = fast_exp2(y1);
 #endif
-            }
-            pk[pr] = pack_bf16(e0, e1);
-            if (pr & 1) acc1 = fma2(pack2(e0, e1), one2, acc1);    // FFMA2 issues faster than FADD2 on sm_100
-            else acc0 = fma2(pack2(e0, e1), one2, acc0);
           }
+          pk[pr] = pack_bf16(e0, e1);
+          if (pr & 1) acc1 = fma2(pack2(e0, e1), one2, acc1);      // FFMA2 issues faster than FADD2 on sm_100
+          else acc0 = fma2(pack2(e0, e1), one2, acc0);
         }
-        if (VP_ATTN_LATE_ODONE && ch == 0 && j > 0 && !waited_o) {                           // P region still read by P_{j-1} V_{j-1}: wait as late
-          mbar_wait_a(a_o_done, (j - 1) & 1);                          // as possible (the first chunk is already computed)
+        if (VP_ATTN_LATE_ODONE && ch == 0 && j > 0 && !waited_o) {   // P region still read by P_{j-1} V_{j-1}: wait as late
+          mbar_wait_a(a_o_done, (j - 1) & 1);                        // as possible (the first chunk is already computed)
           tc_fence_after();
         }
-        tmem_st_x8(tP + ch * 8, pk);
+        if (CP == 4) tmem_st_x4(tP + ch * CP, pk);
+        else if (CP == 8) tmem_st_x8(tP + ch * CP, pk);
+        else tmem_st_x16(tP + ch * CP, pk);
       }
       {
         float a0, a1;

@@ -204,6 +204,9 @@ __device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t* v) {
       VP_W4(v, 4), VP_W4(v, 8), VP_W4(v, 12), VP_W4(v, 16), VP_W4(v, 20), VP_W4(v, 24), VP_W4(v, 28), "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_st_x4(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%4], {%0, %1, %2, %3};\n" ::VP_W4(v, 0), "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t* v) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%8], {%0, %1, %2, %3, %4, %5, %6, %7};\n" ::VP_W4(v, 0), VP_W4(v, 4),
                "r"(taddr)
