@@ -56,8 +56,10 @@ def main():
     x = rn(M, D)
     w_qkv, b_qkv = rn(3 * D, D, sc=0.02), rn(3 * D)
     nq = (rn(64), rn(64))
-    cos = torch.rand(S - St, 64, device=dev); sin = torch.rand(S - St, 64, device=dev)
-    timeit("gemm_qkv", lambda: ops.gemm_qkv(x, w_qkv, b_qkv, M, D, S, H, 0, q, k, v, nq, nq, 1e-6, (cos, sin), St),
+    ang = torch.rand(S - St, 32, device=dev) * 6.28          # pair-repeated tables as the pipeline builds them (EMB:641-642)
+    cos, sin = torch.cos(ang).repeat_interleave(2, 1).contiguous(), torch.sin(ang).repeat_interleave(2, 1).contiguous()
+    pairs = torch.stack([torch.cos(ang), torch.sin(ang)], dim=-1).reshape(S - St, 64).contiguous()
+    timeit("gemm_qkv", lambda: ops.gemm_qkv(x, w_qkv, b_qkv, M, D, S, H, 0, q, k, v, nq, nq, 1e-6, (cos, sin, pairs), St),
            2.0 * M * 3 * D * D, "tflops")
     w_o, b_o = rn(D, D, sc=0.02), rn(D)
     gate = torch.randn(B, 6 * D, device=dev)
