@@ -50,6 +50,10 @@ constexpr uint32_t COL_S = 0, COL_P = 128, COL_O = 192, COL_TILE = 256;
 #ifndef VP_ATTN_POLY_PER16
 #define VP_ATTN_POLY_PER16 0                 // of every 8 element pairs, this many take the polynomial exp2 (0..8)
 #endif
+// (Tried and removed: software pipelining over key tiles — refilling the registers of every finished 16-column chunk with
+//  S(j+1) and scanning its maximum inside the exponentials of tile j.  With ONE S buffer per query tile in TMEM, Q K_{j+2}ᵀ can
+//  then only start when tile j is three quarters done and lands on the critical path: 13.1 ms instead of 8.8 ms.  It needs
+//  a second S buffer, i.e. 64-key tiles or a smaller O — a TMEM-budget redesign.)
 #ifndef VP_ATTN_LEAN_WAIT
 #define VP_ATTN_LEAN_WAIT 0                  // 1: softmax warps spin on try_wait without the watchdog (smaller loop body)
 #endif
