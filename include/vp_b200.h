@@ -102,6 +102,20 @@ int vp_gemm_qkv(const void* a, long long lda, const void* w, long long ldw, cons
                 const void* norm_k_w, const void* norm_k_b, float qk_eps, const float* rope_cos, const float* rope_sin,
                 const float* rope_cs, int text_len, int heads_per_dest, long long dest_stride, void* stream);
 
+/* Step end, one pass over the latent of ONE sample (n elements, bf16 latents as in the pipeline):
+ *   model_output = uncond + guidance * (text - uncond)                     PIPE:981, 995-997 (fp32)
+ *   CogVideoXDPMScheduler.step, prediction_type = "v_prediction"           DPM:386-436 (first / second order)
+ *   latents = bf16(prev_sample); replace_gt re-noise and blend with mask    PIPE:1014-1034 (gt == null: skipped)
+ * Coefficients are the scheduler's per-step scalars (DPM:306-328, 420-422, 451-463), computed by the host in float64 as the
+ * reference does; the *_bf ones must already be rounded to bf16 (they multiply bf16 tensors in the reference, which casts
+ * the 0-dim coefficient to the tensor's dtype first).  mask is [frames, 1, hw] bf16, broadcast over `chan` channels.
+ * Results are bit-identical to the reference's sequence of eager ops. */
+int vp_step_end(const void* noise_pred, float guidance, const void* sample, const float* old_pred, const void* noise,
+                float c_sqrt_alpha_bf, float c_sqrt_beta, float c_m0_bf, float c_m1, float c_m2, float c_m3, float c_mn_bf,
+                int second_order, float* pred_out, float* prev_out, void* latents_out, const void* gt, const void* noise0,
+                const void* mask, int chan, long long hw, float sa_bf, float sb_bf, int renoise, int mask_background, long long n,
+                void* stream);
+
 /* ---- Ulysses over NVLink peer memory: the all-to-all is fused into the producing kernels' epilogues ------------------
  * Every rank of the sequence-parallel group owns a q/k/v buffer [slot][heads/peers][seq_total][64] and an attention-output
  * buffer [peers][seq_total/peers][ldo]; `peer_*` are HOST arrays of DEVICE pointers to all ranks' buffers (own rank included,

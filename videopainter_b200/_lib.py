@@ -34,6 +34,8 @@ SIGNATURES = {
     "vp_attention_peer": [_c_void_p, _c_void_p, _c_void_p, _i, _c_void_p, _c_void_p, _i, _c_void_p, _i, _i, _i, _i, _i, _f, _f,
                           _c_void_p],
     "vp_peer_barrier": [_c_void_p, _i, _i, C.c_uint, _c_void_p],
+    "vp_step_end": [_c_void_p, _f, _c_void_p, _c_void_p, _c_void_p, _f, _f, _f, _f, _f, _f, _f, _i, _c_void_p, _c_void_p, _c_void_p,
+                    _c_void_p, _c_void_p, _c_void_p, _i, _ll, _f, _f, _i, _i, _ll, _c_void_p],
     "vp_peer_scatter": [_c_void_p, _c_void_p, _i, _i, _ll, _c_void_p],
     "vp_peer_alloc": [_ll, _c_void_p, _c_void_p],
     "vp_peer_open": [_c_void_p, _c_void_p],

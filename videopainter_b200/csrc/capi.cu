@@ -228,6 +228,26 @@ int vp_attention_peer(const void* q, const void* k0, const void* v0, int kv_len0
   return launch_attention(q, k0, v0, k1, v1, p, (cudaStream_t)stream);
 }
 
+int vp_step_end(const void* noise_pred, float guidance, const void* sample, const float* old_pred, const void* noise,
+                float c_sqrt_alpha_bf, float c_sqrt_beta, float c_m0_bf, float c_m1, float c_m2, float c_m3, float c_mn_bf,
+                int second_order, float* pred_out, float* prev_out, void* latents_out, const void* gt, const void* noise0,
+                const void* mask, int chan, long long hw, float sa_bf, float sb_bf, int renoise, int mask_background, long long n,
+                void* stream) {
+  VP_REQUIRE(noise_pred && sample && noise && pred_out && latents_out && n > 0, VP_ERR_BAD_SHAPE, "step_end: null pointer");
+  VP_REQUIRE(!second_order || old_pred, VP_ERR_BAD_SHAPE, "step_end: the second-order update needs old_pred");
+  VP_REQUIRE(gt == nullptr || (mask && chan > 0 && hw > 0 && n % ((long long)chan * hw) == 0 && (!renoise || noise0)), VP_ERR_BAD_SHAPE,
+             "step_end: replace_gt needs gt, mask [frames, 1, hw] and n = frames * chan * hw");
+  StepEndParams p{};
+  p.n = n; p.noise_pred = (const __nv_bfloat16*)noise_pred; p.guidance = guidance;
+  p.sample = (const __nv_bfloat16*)sample; p.old_pred = old_pred; p.noise = (const __nv_bfloat16*)noise;
+  p.c_sqrt_alpha_bf = c_sqrt_alpha_bf; p.c_sqrt_beta = c_sqrt_beta; p.c_m0_bf = c_m0_bf; p.c_m1 = c_m1; p.c_m2 = c_m2; p.c_m3 = c_m3;
+  p.c_mn_bf = c_mn_bf; p.second_order = second_order;
+  p.pred_out = pred_out; p.prev_out = prev_out; p.latents_out = (__nv_bfloat16*)latents_out;
+  p.gt = (const __nv_bfloat16*)gt; p.noise0 = (const __nv_bfloat16*)noise0; p.mask = (const __nv_bfloat16*)mask;
+  p.chan = chan; p.hw = hw; p.sa_bf = sa_bf; p.sb_bf = sb_bf; p.renoise = renoise; p.mask_background = mask_background;
+  return launch_step_end(p, (cudaStream_t)stream);
+}
+
 int vp_peer_scatter(const void* src, void* const* peer_dst, int peers, int my_rank, long long bytes_per_peer, void* stream) {
   VP_REQUIRE(src && peer_dst && peers >= 1 && peers <= 8 && my_rank >= 0 && my_rank < peers && bytes_per_peer > 0, VP_ERR_BAD_SHAPE,
              "peer_scatter: bad arguments");

@@ -459,7 +459,50 @@ __global__ void __launch_bounds__(256) peer_scatter_kernel(const uint4* __restri
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Step end: classifier-free-guidance combine (PIPE:995-997), CogVideoXDPMScheduler.step for v-prediction
+// (DPM:386-436) and the replace_gt re-noise / blend (PIPE:1017-1034) in one pass over the latent.  The arithmetic mirrors
+// the reference op by op, including its dtype promotions (a 0-dim coefficient times a bf16 tensor is a bf16 product of the
+// bf16-rounded coefficient), so results are bit-identical; __f*_rn keeps the compiler from contracting into FMAs.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float bf16r(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+__global__ void __launch_bounds__(256) step_end_kernel(const StepEndParams p) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (long long)gridDim.x * blockDim.x) {
+    const float u = __bfloat162float(p.noise_pred[i]), c = __bfloat162float(p.noise_pred[p.n + i]);
+    const float mo = __fadd_rn(u, __fmul_rn(p.guidance, __fsub_rn(c, u)));
+    const float x = __bfloat162float(p.sample[i]);
+    const float pred = __fsub_rn(bf16r(__fmul_rn(x, p.c_sqrt_alpha_bf)), __fmul_rn(mo, p.c_sqrt_beta));
+    float den = pred;
+    if (p.second_order) den = __fsub_rn(__fmul_rn(pred, p.c_m2), __fmul_rn(p.old_pred[i], p.c_m3));
+    const float prev = __fadd_rn(__fsub_rn(bf16r(__fmul_rn(x, p.c_m0_bf)), __fmul_rn(den, p.c_m1)),
+                                 bf16r(__fmul_rn(__bfloat162float(p.noise[i]), p.c_mn_bf)));
+    p.pred_out[i] = pred;
+    if (p.prev_out) p.prev_out[i] = prev;
+    float lat = bf16r(prev);
+    if (p.gt) {
+      float proper = __bfloat162float(p.gt[i]);
+      if (p.renoise)
+        proper = bf16r(__fadd_rn(bf16r(__fmul_rn(proper, p.sa_bf)), bf16r(__fmul_rn(__bfloat162float(p.noise0[i]), p.sb_bf))));
+      const long long f = i / ((long long)p.chan * p.hw);
+      const float m = __bfloat162float(p.mask[f * p.hw + i % p.hw]);
+      const float om = bf16r(__fsub_rn(1.0f, m));
+      lat = p.mask_background ? bf16r(__fadd_rn(bf16r(__fmul_rn(m, proper)), bf16r(__fmul_rn(om, lat))))
+                              : bf16r(__fadd_rn(bf16r(__fmul_rn(om, proper)), bf16r(__fmul_rn(m, lat))));
+    }
+    p.latents_out[i] = __float2bfloat16_rn(lat);
+  }
+}
+
 }  // namespace
+
+int launch_step_end(const StepEndParams& p, cudaStream_t st) {
+  long long blocks = (p.n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  step_end_kernel<<<(unsigned)blocks, 256, 0, st>>>(p);
+  VP_CHECK_CUDA(cudaGetLastError());
+  return VP_OK;
+}
 
 int launch_peer_scatter(const void* src, void* const* peer_dst, int peers, int my_rank, long long bytes_per_peer, cudaStream_t st) {
   PeerPtrs d{};

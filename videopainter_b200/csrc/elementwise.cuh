@@ -23,6 +23,27 @@ struct LnModParams {
   int text_len;                   // rows s < text_len use the text expert
 };
 
+struct StepEndParams {
+  long long n;                               // latent elements of one sample
+  const __nv_bfloat16* noise_pred;           // [2, n]: uncond, text
+  float guidance;
+  const __nv_bfloat16* sample;               // [n]
+  const float* old_pred;                     // [n], read when second_order
+  const __nv_bfloat16* noise;                // [n] the noise the scheduler draws for the branch taken
+  float c_sqrt_alpha_bf, c_sqrt_beta, c_m0_bf, c_m1, c_m2, c_m3, c_mn_bf;   // *_bf: already rounded to bf16
+  int second_order;
+  float* pred_out;                           // [n] pred_original_sample (carried to the next step)
+  float* prev_out;                           // [n] fp32 prev_sample, or null
+  __nv_bfloat16* latents_out;                // [n]
+  const __nv_bfloat16* gt;                   // [n] or null (no replace_gt)
+  const __nv_bfloat16* noise0;               // [n]
+  const __nv_bfloat16* mask;                 // [frames, 1, hw] broadcast over `chan` channels
+  int chan;
+  long long hw;
+  float sa_bf, sb_bf;
+  int renoise, mask_background;
+};
+int launch_step_end(const StepEndParams& p, cudaStream_t st);
 int launch_ln_modulate(const LnModParams& p, cudaStream_t st);
 int launch_gemv(const float* in, const void* W, const void* bias, float* out, int B, int N, int K, int act_silu, cudaStream_t st);
 int launch_timestep_sinusoid(const long long* t_i64, const float* t_f32, float* out, int B, int dim, int flip, float shift,
