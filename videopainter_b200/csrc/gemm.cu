@@ -95,6 +95,31 @@ __device__ __forceinline__ void warp_store_rows64(uint8_t* stage, int lane, cons
   __syncwarp();
 }
 
+// The reverse: every thread wants 64 bytes (32 bf16) of ITS row (src == nullptr: zeros).  The warp fetches whole 64-byte row
+// segments (4 lanes per row) and redistributes through the same swizzled staging buffer.
+__device__ __forceinline__ void warp_load_rows64(uint8_t* stage, int lane, const __nv_bfloat16* src, float* f) {
+  const unsigned long long s = reinterpret_cast<unsigned long long>(src);
+  const int cc = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = i * 8 + (lane >> 2);
+    const unsigned long long sr = __shfl_sync(0xffffffffu, s, r);
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (sr) v = __ldg(reinterpret_cast<const uint4*>(sr + (cc << 4)));
+    *reinterpret_cast<uint4*>(stage + r * 64 + ((cc ^ ((r >> 1) & 3)) << 4)) = v;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint4 u = *reinterpret_cast<const uint4*>(stage + lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4));
+    f[i * 8 + 0] = bf16_lo(u.x); f[i * 8 + 1] = bf16_hi(u.x);
+    f[i * 8 + 2] = bf16_lo(u.y); f[i * 8 + 3] = bf16_hi(u.y);
+    f[i * 8 + 4] = bf16_lo(u.z); f[i * 8 + 5] = bf16_hi(u.z);
+    f[i * 8 + 6] = bf16_lo(u.w); f[i * 8 + 7] = bf16_hi(u.w);
+  }
+  __syncwarp();
+}
+
 __device__ __forceinline__ void pack_bf16x32(const float* f, uint4* u) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -247,8 +272,8 @@ __device__ __forceinline__ void epilogue_cols32(const GemmParams& p, const uint3
   } else if (EPI == EPI_GELU) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
-  } else if (EPI == EPI_RESID && row_ok) {
-    if (p.gate) {
+  } else if (EPI == EPI_RESID) {
+    if (p.gate && row_ok) {
       const float* g = p.gate + (long long)b * p.gate_batch_stride + (s < p.text_len ? p.gate_text_off : p.gate_video_off) + n0;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -257,13 +282,14 @@ __device__ __forceinline__ void epilogue_cols32(const GemmParams& p, const uint3
       }
     }
     float r[32];
-    load_bf16x32(p.res + ((long long)b * p.res_batch_rows + p.res_row_offset + s) * p.ldr + n0, r);
+    warp_load_rows64(stage, lane, row_ok ? p.res + ((long long)b * p.res_batch_rows + p.res_row_offset + s) * p.ldr + n0 : nullptr, r);
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] += r[j];
-    if (p.inject && s >= p.text_len) {
+    if (p.inject) {                                        // warp-uniform; rows that take no injection fetch zeros
       const int sv = s - p.text_len;
-      if (!p.inject_mask || p.inject_mask[(long long)b * p.video_len + sv] == 0) {
-        load_bf16x32(p.inject + (long long)b * p.inject_batch_stride + (long long)sv * p.ldi + n0, r);
+      const bool take = row_ok && s >= p.text_len && (!p.inject_mask || p.inject_mask[(long long)b * p.video_len + sv] == 0);
+      warp_load_rows64(stage, lane, take ? p.inject + (long long)b * p.inject_batch_stride + (long long)sv * p.ldi + n0 : nullptr, r);
+      if (take) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] += r[j];
       }
