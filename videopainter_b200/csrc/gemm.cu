@@ -7,6 +7,8 @@
 //   warp 2   TMEM allocator : 512 columns = two 128x256 accumulator stages
 //   warp 4-7 epilogue       : tcgen05.ld (thread == row), fused epilogue, 16-byte global stores;
 //                             overlaps with the MMAs of the next tile through the second TMEM stage
+#include <stdlib.h>
+
 #include "gemm.cuh"
 #include "host_util.cuh"
 
@@ -57,6 +59,17 @@ __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* p, const float* f) 
   }
 }
 
+#ifndef VP_GEMM_STREAM_STORES
+#define VP_GEMM_STREAM_STORES 0      // 1: epilogue stores carry the .cs (streaming) hint: outputs do not displace A / W in L2
+#endif
+__device__ __forceinline__ void st_global_v4(unsigned long long addr, const uint4& v) {
+#if VP_GEMM_STREAM_STORES
+  asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};\n" ::"l"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+#else
+  *reinterpret_cast<uint4*>(addr) = v;
+#endif
+}
+
 // ---- QKV epilogue on one head (64 accumulator columns) of one row ----------------------------------------------
 // Each thread owns one 128-byte output row (one head of one token).  Storing it directly would make every warp-wide
 // store touch 32 different lines with 16 bytes each — harmless behind the local L2, but over NVLink (peer mode) every
@@ -73,7 +86,7 @@ __device__ __forceinline__ void warp_store_rows128(uint8_t* stage, int lane, con
     const int r = i * 4 + (lane >> 3);
     const uint4 v = *reinterpret_cast<const uint4*>(stage + r * 128 + ((cc ^ (r & 7)) << 4));
     const unsigned long long dr = __shfl_sync(0xffffffffu, d, r);
-    if (dr) *reinterpret_cast<uint4*>(dr + (cc << 4)) = v;
+    if (dr) st_global_v4(dr + (cc << 4), v);
   }
   __syncwarp();
 }
@@ -90,7 +103,7 @@ __device__ __forceinline__ void warp_store_rows64(uint8_t* stage, int lane, cons
     const int r = i * 8 + (lane >> 2);
     const uint4 v = *reinterpret_cast<const uint4*>(stage + r * 64 + ((cc ^ ((r >> 1) & 3)) << 4));
     const unsigned long long dr = __shfl_sync(0xffffffffu, d, r);
-    if (dr) *reinterpret_cast<uint4*>(dr + (cc << 4)) = v;
+    if (dr) st_global_v4(dr + (cc << 4), v);
   }
   __syncwarp();
 }
@@ -508,6 +521,10 @@ int launch_gemm(int epi, const void* A, long long lda, const void* W, long long 
     if (rc) return rc;
   }
   if (q.group_m <= 0) q.group_m = 16;
+  {
+    static const int forced = []() { const char* e = getenv("VP_GEMM_GROUP_M"); return e ? atoi(e) : 0; }();   // tuning aid
+    if (forced > 0) q.group_m = forced;
+  }
   if (q.heads_per_dest <= 0) q.heads_per_dest = q.heads > 0 ? q.heads : 1;
   switch (epi) {
     case EPI_BIAS: return launch_impl<EPI_BIAS>(ta, tb, q, st);
