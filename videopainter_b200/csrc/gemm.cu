@@ -47,16 +47,6 @@ __device__ __forceinline__ void load_bf16x32(const __nv_bfloat16* p, float* f) {
     f[i * 8 + 6] = bf16_lo(u.w); f[i * 8 + 7] = bf16_hi(u.w);
   }
 }
-__device__ __forceinline__ void store_bf16x32(__nv_bfloat16* p, const float* f) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    uint4 u;
-    u.x = pack_bf16(f[i * 8 + 0], f[i * 8 + 1]);
-    u.y = pack_bf16(f[i * 8 + 2], f[i * 8 + 3]);
-    u.z = pack_bf16(f[i * 8 + 4], f[i * 8 + 5]);
-    u.w = pack_bf16(f[i * 8 + 6], f[i * 8 + 7]);
-    reinterpret_cast<uint4*>(p)[i] = u;
-  }
 }
 
 #ifndef VP_GEMM_STREAM_STORES
