@@ -47,7 +47,6 @@ __device__ __forceinline__ void load_bf16x32(const __nv_bfloat16* p, float* f) {
     f[i * 8 + 6] = bf16_lo(u.w); f[i * 8 + 7] = bf16_hi(u.w);
   }
 }
-}
 
 #ifndef VP_GEMM_STREAM_STORES
 #define VP_GEMM_STREAM_STORES 0      // 1: epilogue stores carry the .cs (streaming) hint: outputs do not displace A / W in L2
