@@ -111,11 +111,104 @@ def cpu_block_seconds(repeats: int, seq_video_frames: int = 13) -> float:
     return times[len(times) // 2]
 
 
-def cpu_baseline_record(block_s: float) -> dict:
+def cpu_tiny_step_ms(repeats: int = 20, warmup: int = 3) -> float:
+    """Median time of one branch + transformer step of BASELINE.json configs[0] (tiny: 2 layers, 2x64 heads, 1-layer branch,
+    13x8x8 latent, CFG batch 2, fp32) with the oracle restatement on all host threads (SURVEY.md §8d CPU baseline (i))."""
+    import torch
+    from oracle import cogvideox_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    cfg, cfg_b = O.tiny_config(), O.tiny_config(num_layers=1)
+    sd_t, sd_b = O.init_state_dict(cfg, 11), O.init_state_dict(cfg_b, 12, branch=True)
+    inp = O.make_inputs(cfg, 1)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + repeats):
+            t0 = time.perf_counter()
+            O.denoise_step(sd_t, sd_b, cfg, cfg_b, inp)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    times.sort()
+    return 1e3 * times[len(times) // 2]
+
+
+def cpu_baseline_record(block_s: float, tiny_ms: float = None) -> dict:
     blocks_per_step = (42 + BRANCH_LAYERS) * 2
-    return {"value": 1.0 / (block_s * blocks_per_step), "unit": "steps/s", "cores": os.cpu_count(), "kind": "port",
-            "sample": f"one full-size CogVideoXBlock forward (fp32, batch 1, S=17776) = {block_s:.2f} s on the host; "
-                      f"steps/s = 1 / ({blocks_per_step} block-samples x that), embeds/head ignored"}
+    rec = {"value": 1.0 / (block_s * blocks_per_step), "unit": "steps/s", "cores": os.cpu_count(), "kind": "port",
+           "sample": f"one full-size CogVideoXBlock forward (fp32, batch 1, S=17776) = {block_s:.2f} s on the host; "
+                     f"steps/s = 1 / ({blocks_per_step} block-samples x that), embeds/head ignored"}
+    if tiny_ms is not None:
+        rec["tiny_config_step_ms"] = tiny_ms
+        rec["tiny_config"] = "BASELINE.json configs[0]: 2 layers, 2x64 heads, 1-layer branch, 13x8x8 latent, CFG batch 2, fp32"
+    return rec
+
+
+def source_sha256(names) -> str:
+    import hashlib
+    h = hashlib.sha256()
+    for n in names:
+        with open(os.path.join(ROOT, "videopainter_b200", "csrc", n), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+ATTENTION_SOURCES = ("attention.cu", "attention.cuh", "common.cuh")
+
+
+def gpu_eager_block_ms(dev, batch: int = 2, repeats: int = 3) -> float:
+    """BASELINE ONLY, not on any product path: one full-size CogVideoXBlock (SURVEY.md §3.6 recipe) as the reference executes it —
+    eager bf16 PyTorch, one ATen / cuBLAS call per op, `F.scaled_dot_product_attention` (AP:2192) — on this GPU, random weights.
+    Gives the step a GPU-vs-GPU anchor: the reference's step is 44 of these plus embeds / head."""
+    import torch
+    import torch.nn.functional as F
+    bf16 = torch.bfloat16
+    S, St, D, H = S_TOTAL, S_TEXT, D_MODEL, 48
+    g = torch.Generator(device=dev).manual_seed(5)
+    rnd = lambda *s, sc=1.0: (torch.randn(*s, generator=g, device=dev, dtype=torch.float32) * sc).to(bf16)   # noqa: E731
+    w = {n: rnd(o, i, sc=i ** -0.5) for n, (o, i) in dict(q=(D, D), k=(D, D), v=(D, D), o=(D, D), f1=(4 * D, D), f2=(D, 4 * D),
+                                                          n1=(6 * D, 512), n2=(6 * D, 512)).items()}
+    b = {n: rnd(t.shape[0], sc=0.02) for n, t in w.items()}
+    ln = {n: (1 + rnd(d, sc=0.1), rnd(d, sc=0.1)) for n, d in dict(n1=D, n2=D, nq=64, nk=64).items()}
+    from videopainter_b200.rope import pipeline_rope
+    cos, sin = (t.to(dev) for t in pipeline_rope(64, 480, 720, 13))
+    h, e, temb = rnd(batch, S - St, D), rnd(batch, St, D), rnd(batch, 512)
+
+    def norm_zero(n, h, e):                                           # NRM:373-379
+        sh, sc, gt, esh, esc, egt = F.linear(F.silu(temb), w[n], b[n]).chunk(6, dim=1)
+        h = F.layer_norm(h, (D,), *ln[n], 1e-5) * (1 + sc)[:, None] + sh[:, None]
+        e = F.layer_norm(e, (D,), *ln[n], 1e-5) * (1 + esc)[:, None] + esh[:, None]
+        return h, e, gt[:, None], egt[:, None]
+
+    def rope(x):                                                      # EMB:675-692
+        xr, xi = x.reshape(*x.shape[:-1], -1, 2).unbind(-1)
+        rot = torch.stack([-xi, xr], dim=-1).flatten(3)
+        return (x.float() * cos + rot.float() * sin).to(x.dtype)
+
+    def block(h, e):                                                  # T3D:125-184, AP:2107-2209
+        nh, ne, gt, egt = norm_zero("n1", h, e)
+        x = torch.cat([ne, nh], dim=1)
+        q, k, v = (F.linear(x, w[n], b[n]).view(batch, S, H, 64).transpose(1, 2) for n in "qkv")
+        q, k = F.layer_norm(q, (64,), *ln["nq"], 1e-6), F.layer_norm(k, (64,), *ln["nk"], 1e-6)
+        q[:, :, St:] = rope(q[:, :, St:])
+        k[:, :, St:] = rope(k[:, :, St:])
+        o = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(batch, S, D)
+        o = F.linear(o, w["o"], b["o"])
+        h, e = h + gt * o[:, St:], e + egt * o[:, :St]
+        nh, ne, gt, egt = norm_zero("n2", h, e)
+        f = F.linear(F.gelu(F.linear(torch.cat([ne, nh], dim=1), w["f1"], b["f1"]), approximate="tanh"), w["f2"], b["f2"])
+        return h + gt * f[:, St:], e + egt * f[:, :St]
+
+    times = []
+    with torch.no_grad():
+        for i in range(repeats + 1):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            block(h, e)
+            e1.record()
+            torch.cuda.synchronize()
+            if i > 0:
+                times.append(e0.elapsed_time(e1))
+    times.sort()
+    return times[len(times) // 2]
 
 
 def run_reference(args) -> None:
@@ -128,7 +221,7 @@ def run_reference(args) -> None:
         if i >= args.warmup:
             times.append(t)
     block_s = sum(times) / len(times)
-    rec = cpu_baseline_record(block_s)
+    rec = cpu_baseline_record(block_s, cpu_tiny_step_ms())
     out = {"impl": "reference", "metric": "denoise steps/s (49x480x720, CFG)", "value": rec["value"], "unit": "steps/s",
            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / rec["value"],
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
@@ -150,6 +243,7 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--layers", type=int, default=42, help="(debug only) fewer layers -> line is marked invalid")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-eager", action="store_true")
     ap.add_argument("--breakdown", default=None, help="write the per-kernel breakdown JSON to this path")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -222,45 +316,54 @@ def main() -> None:
         torch.cuda.synchronize()
 
     resident = {k: v.to(dev) for k, v in host.items()}
-    with torch.no_grad():
-        for _ in range(args.warmup):
-            step(resident)
-        # ---------------- device-resident timing (value) ----------------
+    import hashlib
+
+    def timed(fn):
+        """K calls of fn between a barrier + synchronize on both sides; CUDA events on the launching stream; max over ranks."""
         barrier()
-        sampler = ClockSampler(local)
-        sampler.start()
-        launches0 = ops.launch_count
-        ops.start_profile()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.cudart().cudaProfilerStart()      # `ncu --profile-from-start off` then lists exactly the timed steps
         e0.record()
         for _ in range(args.steps):
-            step(resident)
+            fn()
         e1.record()
         barrier()
-        torch.cuda.cudart().cudaProfilerStop()
-        clocks = sampler.stop()
-        prof = ops.stop_profile()
-        launches = ops.launch_count - launches0
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        ms_per_step = ms.item() / args.steps
+        return ms.item() / args.steps
 
+    last = {}
+
+    def resident_step():
+        last["noise"] = step(resident)
+
+    def e2e_step():
+        d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        noise = step(d)
+        out_host.copy_(noise.float(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            step(resident)
+        # ---------------- device-resident timing (value): no per-op events, nothing but the step's own launches ----------------
+        sampler = ClockSampler(local)
+        sampler.start()
+        launches0 = ops.launch_count
+        torch.cuda.cudart().cudaProfilerStart()      # `ncu --profile-from-start off` then lists exactly the timed steps
+        ms_per_step = timed(resident_step)
+        torch.cuda.cudart().cudaProfilerStop()
+        clocks = sampler.stop()
+        launches = ops.launch_count - launches0
+        # every rank holds the complete noise prediction; its SHA-256 must not depend on N (sharded == single GPU, bit for bit)
+        noise_sha = hashlib.sha256(last["noise"].contiguous().view(torch.int16).cpu().numpy().tobytes()).hexdigest()
+        noise_absmax = float(last["noise"].float().abs().max())
         # ---------------- end-to-end timing: host buffers in, host result out ----------------
-        barrier()
-        e0.record()
-        for _ in range(args.steps):
-            d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-            noise = step(d)
-            out_host.copy_(noise.float(), non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-        e1.record()
-        barrier()
-        ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-        e2e_ms = ms2.item() / args.steps
+        e2e_ms = timed(e2e_step)
+        # ---------------- per-kernel pass: the same K steps with CUDA events around every launch (roofline / breakdown) --------
+        ops.start_profile()
+        prof_ms_per_step = timed(resident_step)
+        prof = ops.stop_profile()
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     d2h = out_host.numel() * out_host.element_size()
 
@@ -282,23 +385,29 @@ def main() -> None:
         breakdown[name] = {"launches": n, "ms_per_step": t / args.steps, "share": t / tot_ms if tot_ms else 0.0,
                            "avg_launch_ms": t / n, "tflops": (w / (t * 1e-3) / 1e12) if (w and name != "ln_modulate") else None,
                            "gbs": (w / (t * 1e-3) / 1e9) if name == "ln_modulate" else None}
-    # DRAM traffic of the dominant kernel per launch: from the committed ncu --set full capture (same shape, one launch)
-    traffic = None
+    # DRAM traffic of the dominant kernel per launch: from the committed ncu --set full capture of one launch at this shape —
+    # only if that capture was taken from the kernel source that is built now (source hash recorded with the capture)
+    traffic, traffic_note = None, "no ncu --set full capture of the current attention kernel source is committed"
     try:
         ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_attention_latest.json")))
         to_bytes = lambda v: float(v.split()[0]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[v.split()[1]]   # noqa: E731
-        traffic = (to_bytes(ncu["dram__bytes_read.sum"]) + to_bytes(ncu["dram__bytes_write.sum"]))
+        if ncu.get("source_sha256") == source_sha256(ATTENTION_SOURCES):
+            traffic = (to_bytes(ncu["dram__bytes_read.sum"]) + to_bytes(ncu["dram__bytes_write.sum"]))
+            traffic_note = ("dram__bytes_read.sum + dram__bytes_write.sum of one attention launch (B=2, 48 heads, S=17776) from "
+                            "profiles/ncu_attention_latest.json (same kernel source, sha256 checked); algorithmic q+k+v+o bytes = 873.6 MB")
+        else:
+            traffic_note = "profiles/ncu_attention_latest.json was captured from a different attention kernel source: dropped"
     except Exception:
-        traffic = None
+        pass
     dom = max(prof.items(), key=lambda kv: kv[1][1])
     dn, (n_l, t_l, w_l) = dom
     achieved = w_l / (t_l * 1e-3) / 1e12
     roofline = {"kernel": dn, "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved / peak_tf, "traffic": traffic if (dn == "attention" and world == 1) else None,
-                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one attention launch (B=2, 48 heads, S=17776) from "
-                                "profiles/ncu_attention_latest.json; algorithmic q+k+v+o bytes = 873.6 MB",
-                "peak_source": peak_src,
-                "flops_per_launch": w_l / n_l, "avg_launch_ms": t_l / n_l, "share_of_step": t_l / tot_ms}
+                "traffic_note": traffic_note, "peak_source": peak_src,
+                "flops_per_launch": w_l / n_l, "avg_launch_ms": t_l / n_l, "share_of_step": t_l / tot_ms,
+                "timed_in": f"a separate pass of the same {args.steps} steps with CUDA events around every launch "
+                            f"({prof_ms_per_step:.1f} ms/step with events vs {ms_per_step:.1f} without)"}
     flops = step_flops(B_global, args.layers + BRANCH_LAYERS)
     out = {"metric": "denoise steps/s (49x480x720, CFG)", "value": 1000.0 / ms_per_step, "unit": "steps/s", "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -314,15 +423,27 @@ def main() -> None:
                                  "burst": flops / (ms_per_step * 1e-3) / 1e12 / (peaks.get("bf16_tflops", 1650.0) * world),
                                  "note": "whole-job algorithmic FLOP/s over n_gpus x the measured cuBLAS peak"},
            "roofline": roofline, "clocks": clocks, "gpu_launches": launches,
+           "noise_sha256": noise_sha, "noise_absmax": noise_absmax,
            "e2e": {"value": 1000.0 / e2e_ms, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                    "ms_per_step": e2e_ms}}
     if args.layers != 42:
         out["invalid"] = "debug run with fewer layers than the named config"
     if not args.no_cpu_baseline and world == 1:
-        out["cpu_baseline"] = cpu_baseline_record(cpu_block_seconds(1))
+        out["cpu_baseline"] = cpu_baseline_record(cpu_block_seconds(1), cpu_tiny_step_ms())
+    if not args.no_gpu_eager and world == 1:
+        try:
+            blk = gpu_eager_block_ms(dev)
+            out["gpu_eager_reference"] = {
+                "block_ms": blk, "steps_per_s_extrapolated": 1000.0 / (blk * (42 + BRANCH_LAYERS)),
+                "what": "BASELINE ONLY: one full-size CogVideoXBlock (CFG batch 2, S=17776) in eager bf16 PyTorch with "
+                        "F.scaled_dot_product_attention, as the reference executes it, on this GPU; x 44 blocks, embeds / head "
+                        "ignored; random weights"}
+        except Exception as e:   # noqa: BLE001 - a baseline must never break the measurement
+            out["gpu_eager_reference"] = {"unavailable": str(e)[:200]}
     if args.breakdown:
         with open(args.breakdown, "w") as f:
-            json.dump({"ms_per_step": ms_per_step, "kernels": breakdown, "clocks": clocks}, f, indent=1)
+            json.dump({"ms_per_step": ms_per_step, "ms_per_step_with_events": prof_ms_per_step, "kernels": breakdown,
+                       "clocks": clocks}, f, indent=1)
     emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
