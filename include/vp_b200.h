@@ -134,6 +134,12 @@ int vp_attention_peer(const void* q, const void* k0, const void* v0, int kv_len0
                       void* const* peer_out, int peers, int my_rank, int ldo, int heads, int seq_q, float softmax_scale,
                       float out_scale, void* stream);
 int vp_peer_barrier(void* const* peer_flags, int peers, int my_rank, unsigned int epoch, void* stream);
+/* The barrier's wait is bounded (default 20 000 ms, or the environment variable VP_B200_PEER_TIMEOUT_MS at first use; 0 = wait
+ * for ever): a rank whose peers do not show up in time adds one to 32-bit word 8 of ITS flag buffer (the buffers are 64
+ * bytes: words 0..7 = epochs written by the peers, word 8 = time-out count) and lets the stream continue — no trap, no
+ * sticky CUDA error; the host reads the word whenever it likes.  Kernel-replay profilers (ncu) stall single ranks for
+ * longer than any sensible bound: profile peer mode with the timeout set to 0 and `--replay-mode application`. */
+int vp_peer_set_timeout_ms(long long ms);
 /* Alternative to vp_attention_peer: chunk d (bytes_per_peer bytes) of the local buffer `src` is copied into slot my_rank of
  * rank d's buffer peer_dst[d] ([peers][bytes_per_peer]) by one kernel of 16-byte peer stores (whole lines per warp). */
 int vp_peer_scatter(const void* src, void* const* peer_dst, int peers, int my_rank, long long bytes_per_peer, void* stream);

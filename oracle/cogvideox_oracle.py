@@ -382,10 +382,33 @@ def block(sd, pre, cfg: OracleConfig, h, e, temb, rope, resample=False, resample
     return h, e
 
 
+def block_wo_text(sd, pre, cfg: OracleConfig, h, temb, rope, head_chunk=0):
+    """CogVideoXBlock.forward_wo_text T3D:186-216 with CogVideoXLayerNormZero.forward_wo_text NRM:381-386 (the video triple
+    shift, scale, gate) and CogVideoXAttnProcessor2_0_wo_text AP:2316-2366 (video tokens only, RoPE on every token)."""
+    H, D = cfg.num_attention_heads, h.shape[-1]
+
+    def norm(name):
+        sh, sc, g = _lin(sd, pre + name + ".linear", F.silu(temb)).chunk(6, dim=1)[:3]
+        w, b = sd[pre + name + ".norm.weight"], sd[pre + name + ".norm.bias"]
+        return F.layer_norm(h, (D,), w, b, cfg.norm_eps) * (1 + sc)[:, None, :] + sh[:, None, :], g[:, None, :]
+
+    nh, g = norm("norm1")
+    a = pre + "attn1"
+    q = _qk_norm(sd, a + ".norm_q", _heads(_lin(sd, a + ".to_q", nh), H))
+    k = _qk_norm(sd, a + ".norm_k", _heads(_lin(sd, a + ".to_k", nh), H))
+    v = _heads(_lin(sd, a + ".to_v", nh), H)
+    if rope is not None:
+        q, k = apply_rope(q, *rope), apply_rope(k, *rope)
+    o = sdpa(q, k, v, head_chunk).transpose(1, 2).reshape(h.shape[0], -1, cfg.inner_dim)
+    h = h + g * _lin(sd, a + ".to_out.0", o)
+    nh, g = norm("norm2")
+    return h + g * _lin(sd, pre + "ff.net.2", F.gelu(_lin(sd, pre + "ff.net.0.proj", nh), approximate="tanh"))
+
+
 def branch_forward(sd, cfg: OracleConfig, hidden_states: Tensor, encoder_hidden_states: Tensor,
                    branch_cond: Tensor, timestep: Tensor, rope, conditioning_scale: float = 1.0,
-                   head_chunk: int = 0) -> List[Tensor]:
-    """CogvideoXBranchModel.forward BR:295-434 (wo_text=False path)."""
+                   head_chunk: int = 0, wo_text: bool = False) -> List[Tensor]:
+    """CogvideoXBranchModel.forward BR:295-434; wo_text=True takes BR:407-412 (a branch built with wo_text=True)."""
     dtype = hidden_states.dtype
     temb = timestep_embedding(sd, cfg, timestep, dtype)
     cond = torch.cat([hidden_states, branch_cond], dim=-3)                # BR:359
@@ -394,7 +417,10 @@ def branch_forward(sd, cfg: OracleConfig, hidden_states: Tensor, encoder_hidden_
     e, h = x[:, :St], x[:, St:]
     samples = []
     for i in range(cfg.num_layers):
-        h, e = block(sd, f"transformer_blocks.{i}.", cfg, h, e, temb, rope, head_chunk=head_chunk)
+        if wo_text:
+            h = block_wo_text(sd, f"transformer_blocks.{i}.", cfg, h, temb, rope, head_chunk=head_chunk)
+        else:
+            h, e = block(sd, f"transformer_blocks.{i}.", cfg, h, e, temb, rope, head_chunk=head_chunk)
         samples.append(h)
     out = [_lin(sd, f"branch_blocks.{i}", s) for i, s in enumerate(samples)]
     return [(s * conditioning_scale).to(dtype) for s in out]
@@ -405,8 +431,11 @@ def transformer_forward(sd, cfg: OracleConfig, hidden_states: Tensor, encoder_hi
                         branch_block_masks: Optional[Tensor] = None, add_first: bool = False,
                         attention_kwargs: Optional[dict] = None, return_hidden_states: bool = False,
                         return_resample_mask: bool = False, id_pool_resample_learnable: bool = False,
-                        head_chunk: int = 0):
+                        head_chunk: int = 0, fused_qkv: bool = False):
     """CogVideoXTransformer3DModel.forward T3D:472-646 with return_dict=False.
+    ``fused_qkv``: after fuse_qkv_projections() (T3D:433-456) every block runs FusedCogVideoXAttnProcessor2_0 (AP:2378-2436):
+    plain joint attention — no resample mask and no previous-window states (Attention.forward drops kwargs the processor's
+    signature lacks, AP:479-488).
     ``cfg.id_pool_resample_learnable`` selects the processor (construction-time, T3D:98-99); the
     call-time flag of the same name only controls mask building (T3D:534)."""
     B, Fr, C, H, W = hidden_states.shape
@@ -437,8 +466,10 @@ def transformer_forward(sd, cfg: OracleConfig, hidden_states: Tensor, encoder_hi
             if prev is not None:
                 prev_w = kw["prev_clip_weight"]
             prev_mask = kw.get("prev_resample_mask")
+        if fused_qkv:
+            prev = prev_w = prev_mask = None
         h, e = block(sd, f"transformer_blocks.{i}.", cfg, h, e, temb, rope,
-                     resample=cfg.id_pool_resample_learnable, resample_mask=resample_mask,
+                     resample=cfg.id_pool_resample_learnable and not fused_qkv, resample_mask=resample_mask,
                      prev=prev, prev_w=prev_w, prev_mask=prev_mask, head_chunk=head_chunk)
         if branch_block_samples is not None:                             # T3D:596-609
             if not add_first:

@@ -121,9 +121,57 @@ def run_block_case():
     print("block_full_width ->", path, os.path.getsize(path) // 1024, "KiB")
 
 
+@torch.no_grad()
+def run_variants():
+    """Corners of the reference the first two cases do not reach: window 2 with prev_clip_weight == 0.0 (T3D:141-146
+    still normalises the previous states, both processors then ignore them: AP:2156, 2247), add_first=True WITH masks
+    (T3D:600-609), the wo_text branch (BR:407-412 on a branch built with wo_text=True) and fused QKV projections (T3D:433-456)
+    on a model built with the resample processor.  Outputs of the real reference modules."""
+    rec = dict(case="tiny_variants", seed_t=11, seed_b=12, seed_in=1)
+    for resample in (False, True):
+        cfg, cfg_b = O.tiny_config(id_pool_resample_learnable=resample), O.tiny_config(num_layers=1)
+        tr, br, sd_t, sd_b = build_reference(cfg, cfg_b, 11, 12)
+        inp, inp2 = O.make_inputs(cfg, seed=1), O.make_inputs(cfg, seed=2)
+
+        def step(i, kw=None, add_first=False, model=tr):
+            lat = torch.cat([i["latents"], i["image_latents"]], dim=2)
+            cond = torch.cat([i["masked_latents"], i["mask"]], dim=2)
+            smp = br(hidden_states=i["latents"], encoder_hidden_states=i["text"], branch_cond=cond, timestep=i["timestep"],
+                     image_rotary_emb=i["rope"], return_dict=False)[0]
+            return model(hidden_states=lat, encoder_hidden_states=i["text"], timestep=i["timestep"], image_rotary_emb=i["rope"],
+                         branch_block_samples=smp, attention_kwargs=kw, branch_block_masks=i["mask"][:, :, :1], add_first=add_first,
+                         return_hidden_states=True, return_resample_mask=True, return_dict=False)
+        out, hs, rmask = step(inp)
+        kw = dict(prev_hidden_states={i: h for i, h in enumerate(hs)}, prev_clip_weight=0.0, prev_resample_mask=rmask)
+        tag = "resample" if resample else "plain"
+        rec[f"w2_prev0_{tag}"] = step(inp2, kw)[0].clone()
+        rec[f"add_first_masked_{tag}"] = step(inp, add_first=True)[0].clone()
+        if resample:
+            tr.fuse_qkv_projections()
+            kw = dict(prev_hidden_states={i: h for i, h in enumerate(hs)}, prev_clip_weight=0.5, prev_resample_mask=rmask)
+            rec["fused_qkv_w2"] = step(inp2, kw)[0].clone()
+            tr.unfuse_qkv_projections()
+    # wo_text branch
+    _, BR = import_reference()
+    cfg_b = O.tiny_config(num_layers=2)
+    sd_b = O.init_state_dict(cfg_b, 13, branch=True)
+    brw = BR(**ref_kwargs(cfg_b), wo_text=True).eval()
+    brw.load_state_dict(sd_b, strict=True)
+    inp = O.make_inputs(cfg_b, seed=1)
+    cond = torch.cat([inp["masked_latents"], inp["mask"]], dim=2)
+    smp = brw(hidden_states=inp["latents"], encoder_hidden_states=inp["text"], branch_cond=cond, timestep=inp["timestep"],
+              image_rotary_emb=inp["rope"], conditioning_scale=0.7, wo_text=True, return_dict=False)[0]
+    rec["wo_text_samples"] = [s.clone() for s in smp]
+    rec["wo_text_seed_b"] = 13
+    path = os.path.join(ROOT, "tests", "golden", "tiny_variants.pt")
+    torch.save(rec, path)
+    print("tiny_variants ->", path, os.path.getsize(path) // 1024, "KiB")
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count())
     run_case("tiny_step", resample=False, two_windows=True, prev_w=0.5)
     run_case("tiny_step_resample", resample=True, two_windows=True, prev_w=0.5)
     run_block_case()
+    run_variants()

@@ -38,6 +38,10 @@ class ThreadRuntime(parallel.Runtime):
         self._sync()
         self.fabric.barrier.wait()
 
+    def release_shared(self, allocations):
+        self._sync()
+        self.fabric.barrier.wait()
+
     def peer_barrier(self, flag_ptrs, epoch):
         # kernels of different virtual ranks share one GPU: they must not spin on each other, so the barrier is host-side
         self._sync()

@@ -90,3 +90,47 @@ def test_oracle_matches_live_reference_pos_tables():
                              sample_height=8, sample_frames=49, max_text_seq_length=16,
                              use_positional_embeddings=False, use_learned_positional_embeddings=True)
     assert torch.equal(pe.pos_embedding, O.sincos_pos_embedding(cfg))
+
+
+def test_oracle_matches_reference_variant_goldens():
+    """tests/golden/tiny_variants.pt (oracle/make_golden.py run_variants, outputs of the real reference): window 2 with
+    prev_clip_weight == 0.0, add_first with masks, fused QKV projections, the wo_text branch."""
+    rec = torch.load(os.path.join(GOLD, "tiny_variants.pt"))
+    for resample in (False, True):
+        cfg, cfg_b = O.tiny_config(id_pool_resample_learnable=resample), O.tiny_config(num_layers=1)
+        sd_t = O.init_state_dict(cfg, rec["seed_t"])
+        sd_b = O.init_state_dict(cfg_b, rec["seed_b"], branch=True)
+        inp, inp2 = O.make_inputs(cfg, rec["seed_in"]), O.make_inputs(cfg, 2)
+        tag = "resample" if resample else "plain"
+        with torch.no_grad():
+            _, (out, hs, rmask) = O.denoise_step(sd_t, sd_b, cfg, cfg_b, inp)
+            kw = dict(prev_hidden_states={i: h for i, h in enumerate(hs)}, prev_clip_weight=0.0, prev_resample_mask=rmask)
+            _, (out2, _, _) = O.denoise_step(sd_t, sd_b, cfg, cfg_b, inp2, attention_kwargs=kw)
+            torch.testing.assert_close(out2, rec[f"w2_prev0_{tag}"], **TOL)
+            # prev_clip_weight == 0.0 must equal running window 2 with no previous states at all (SURVEY §3.7)
+            _, (out2n, _, _) = O.denoise_step(sd_t, sd_b, cfg, cfg_b, inp2)
+            torch.testing.assert_close(out2, out2n, rtol=0, atol=0)
+            lat = torch.cat([inp["latents"], inp["image_latents"]], dim=2)
+            cond = torch.cat([inp["masked_latents"], inp["mask"]], dim=2)
+            smp = O.branch_forward(sd_b, cfg_b, inp["latents"], inp["text"], cond, inp["timestep"], inp["rope"])
+            outa = O.transformer_forward(sd_t, cfg, lat, inp["text"], inp["timestep"], inp["rope"], smp, inp["mask"][:, :, :1],
+                                         add_first=True, return_hidden_states=True, return_resample_mask=True)[0]
+            torch.testing.assert_close(outa, rec[f"add_first_masked_{tag}"], **TOL)
+            if resample:
+                lat2 = torch.cat([inp2["latents"], inp2["image_latents"]], dim=2)
+                cond2 = torch.cat([inp2["masked_latents"], inp2["mask"]], dim=2)
+                smp2 = O.branch_forward(sd_b, cfg_b, inp2["latents"], inp2["text"], cond2, inp2["timestep"], inp2["rope"])
+                kw = dict(prev_hidden_states={i: h for i, h in enumerate(hs)}, prev_clip_weight=0.5, prev_resample_mask=rmask)
+                outf = O.transformer_forward(sd_t, cfg, lat2, inp2["text"], inp2["timestep"], inp2["rope"], smp2,
+                                             inp2["mask"][:, :, :1], attention_kwargs=kw, return_hidden_states=True,
+                                             return_resample_mask=True, fused_qkv=True)[0]
+                torch.testing.assert_close(outf, rec["fused_qkv_w2"], **TOL)
+    cfg_b = O.tiny_config(num_layers=2)
+    sd_b = O.init_state_dict(cfg_b, rec["wo_text_seed_b"], branch=True)
+    inp = O.make_inputs(cfg_b, rec["seed_in"])
+    cond = torch.cat([inp["masked_latents"], inp["mask"]], dim=2)
+    with torch.no_grad():
+        smp = O.branch_forward(sd_b, cfg_b, inp["latents"], inp["text"], cond, inp["timestep"], inp["rope"], conditioning_scale=0.7,
+                               wo_text=True)
+    for a, b in zip(smp, rec["wo_text_samples"]):
+        torch.testing.assert_close(a, b, **TOL)

@@ -1,6 +1,6 @@
 """videopainter_b200 — B200-native (sm_100a) denoising hot path of VideoPainter: CogVideoX-5B-I2V backbone forward plus the
 context-encoder branch, behind the reference's model `forward` signatures.  See DESIGN.md / INTEGRATION.md."""
-from .models import (CogVideoXTransformer3DModel, CogvideoXBranchModel, install, uninstall)  # noqa: F401
+from .models import (CogVideoXTransformer3DModel, CogvideoXBranchModel, install, uninstall, invalidate)  # noqa: F401
 from . import engine, ops, parallel, step_end  # noqa: F401
 
-__all__ = ["CogVideoXTransformer3DModel", "CogvideoXBranchModel", "install", "uninstall", "engine", "ops", "parallel", "step_end"]
+__all__ = ["CogVideoXTransformer3DModel", "CogvideoXBranchModel", "install", "uninstall", "invalidate", "engine", "ops", "parallel", "step_end"]

@@ -41,6 +41,7 @@ SIGNATURES = {
     "vp_peer_open": [_c_void_p, _c_void_p],
     "vp_peer_close": [_c_void_p],
     "vp_peer_free": [_c_void_p],
+    "vp_peer_set_timeout_ms": [_ll],
     "vp_a2a_unpack_heads": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _i, _i, _i, _i, _c_void_p],
     "vp_attention": [_c_void_p, _c_void_p, _c_void_p, _i, _c_void_p, _c_void_p, _i, _c_void_p, _i, _i, _i, _i, _f, _f, _i,
                      _c_void_p],

@@ -20,6 +20,7 @@ struct AttnParams {
   __nv_bfloat16* peer_out[8];
   int peer_rows;
   int peer_src;
+  float one;                 // 1.0f, set by the launcher (a multiplier the compiler cannot fold: keeps packed adds on FFMA2)
 };
 
 int launch_attention(const void* q, const void* k0, const void* v0, const void* k1, const void* v1, const AttnParams& p,

@@ -297,6 +297,8 @@ int vp_peer_free(void* ptr) {
   return VP_OK;
 }
 
+int vp_peer_set_timeout_ms(long long ms) { return set_peer_timeout_ms(ms); }
+
 int vp_peer_barrier(void* const* peer_flags, int peers, int my_rank, unsigned int epoch, void* stream) {
   VP_REQUIRE(peer_flags && peers >= 1 && peers <= 8 && my_rank >= 0 && my_rank < peers, VP_ERR_BAD_SHAPE, "peer_barrier: bad arguments");
   uint32_t* f[8];

@@ -196,6 +196,12 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t* v) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : VP_R4(v, 0), VP_R4(v, 4)
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t* v) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%32], "

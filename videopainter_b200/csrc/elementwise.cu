@@ -3,6 +3,10 @@
 // 2x2/stride-2 patch-embed convolution (EMB:408-414), mask pooling (EMB:417-426), the final double LayerNorm
 // (T3D:613-624) and unpatchify (T3D:630-632).
 #include "elementwise.cuh"
+
+#include <stdlib.h>
+
+#include <atomic>
 #include "host_util.cuh"
 
 namespace vp {
@@ -422,9 +426,11 @@ __global__ void __launch_bounds__(256) a2a_unpack_heads_kernel(const uint4* __re
 
 // Cross-GPU barrier over peer memory: every rank runs one of these on its own GPU.  Thread i tells rank i "rank my_rank has
 // reached epoch" (release store into rank i's flag array, after a system-scope fence that orders this GPU's earlier peer
-// stores), then waits until rank i has said the same to us.  Bounded: a lost peer traps after ~4 s instead of hanging.
+// stores), then waits until rank i has said the same to us.  Bounded (timeout_ns, 0 = never): a rank that runs out of time
+// counts the event in word kPeerErrWord of its own flag buffer and carries on — the host decides what to do; nothing traps.
 struct PeerFlags { uint32_t* p[8]; };
-__global__ void peer_barrier_kernel(PeerFlags flags, int peers, int my_rank, uint32_t epoch) {
+constexpr int kPeerErrWord = 8;
+__global__ void peer_barrier_kernel(PeerFlags flags, int peers, int my_rank, uint32_t epoch, unsigned long long timeout_ns) {
   const int i = threadIdx.x;
   if (i >= peers) return;
   __threadfence_system();
@@ -439,7 +445,10 @@ __global__ void peer_barrier_kernel(PeerFlags flags, int peers, int my_rank, uin
     if ((++spins & 0xfff) == 0) {
       const uint64_t now = global_timer_ns();
       if (t0 == 0) t0 = now;
-      else if (now - t0 > 4000000000ull) __trap();
+      else if (timeout_ns != 0 && now - t0 > timeout_ns) {
+        atomicAdd(flags.p[my_rank] + kPeerErrWord, 1u);
+        break;
+      }
     }
   }
   __threadfence_system();
@@ -516,10 +525,25 @@ int launch_peer_scatter(const void* src, void* const* peer_dst, int peers, int m
   return VP_OK;
 }
 
+static std::atomic<long long>& peer_timeout_ms() {
+  static std::atomic<long long> v{[]() -> long long {
+    const char* e = getenv("VP_B200_PEER_TIMEOUT_MS");
+    return e ? atoll(e) : 20000ll;
+  }()};
+  return v;
+}
+
+int set_peer_timeout_ms(long long ms) {
+  if (ms < 0) return fail(VP_ERR_BAD_SHAPE, "peer_set_timeout_ms: negative timeout");
+  peer_timeout_ms().store(ms);
+  return VP_OK;
+}
+
 int launch_peer_barrier(uint32_t* const* peer_flags, int peers, int my_rank, uint32_t epoch, cudaStream_t st) {
   PeerFlags f{};
   for (int i = 0; i < peers; ++i) f.p[i] = peer_flags[i];
-  peer_barrier_kernel<<<1, 32, 0, st>>>(f, peers, my_rank, epoch);
+  const unsigned long long timeout_ns = (unsigned long long)peer_timeout_ms().load() * 1000000ull;
+  peer_barrier_kernel<<<1, 32, 0, st>>>(f, peers, my_rank, epoch, timeout_ns);
   VP_CHECK_CUDA(cudaGetLastError());
   return VP_OK;
 }
@@ -578,12 +602,9 @@ int launch_ln_modulate(const LnModParams& p, cudaStream_t st) {
   if (stages > LN_MAX_STAGES) stages = LN_MAX_STAGES;
   if (stages < 1) stages = 1;
   const size_t smem = (size_t)stages * stage_bytes;
-  static bool configured = false;
-  if (!configured) {
-    VP_CHECK_CUDA(cudaFuncSetAttribute(ln_modulate_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, LN_SMEM_BUDGET));
-    VP_CHECK_CUDA(cudaFuncSetAttribute(ln_modulate_kernel<LN_MAX_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, LN_SMEM_BUDGET));
-    configured = true;
-  }
+  int rc_cfg;
+  if ((rc_cfg = configure_once(reinterpret_cast<const void*>(ln_modulate_kernel<12>), LN_SMEM_BUDGET))) return rc_cfg;
+  if ((rc_cfg = configure_once(reinterpret_cast<const void*>(ln_modulate_kernel<LN_MAX_WARPS>), LN_SMEM_BUDGET))) return rc_cfg;
   if (threads <= 12 * 32) ln_modulate_kernel<12><<<(unsigned)grid, threads, smem, st>>>(q, units_text, units_video, stages);
   else ln_modulate_kernel<LN_MAX_WARPS><<<(unsigned)grid, threads, smem, st>>>(q, units_text, units_video, stages);
   VP_CHECK_CUDA(cudaGetLastError());

@@ -53,6 +53,7 @@ int launch_mask_pool(const void* mask, int BF, int H, int W, uint8_t* out, cudaS
 int launch_a2a_unpack_heads(const void* src, void* const* dst, int slots, int peers, int heads_local, int rows_per_peer,
                             cudaStream_t st);
 int launch_peer_scatter(const void* src, void* const* peer_dst, int peers, int my_rank, long long bytes_per_peer, cudaStream_t st);
+int set_peer_timeout_ms(long long ms);
 int launch_peer_barrier(uint32_t* const* peer_flags, int peers, int my_rank, uint32_t epoch, cudaStream_t st);
 int launch_unpatchify(const void* proj, int BF, int C, int H, int W, void* out, cudaStream_t st);
 

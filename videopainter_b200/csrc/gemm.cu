@@ -466,11 +466,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
 template <int EPI>
 int launch_impl(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    VP_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    configured = true;
-  }
+  const int rc_cfg = configure_once(reinterpret_cast<const void*>(gemm_bf16_kernel<EPI>), SMEM_BYTES);
+  if (rc_cfg) return rc_cfg;
   const int m_tiles = (p.M + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN;
   const int sms = sm_count();
   if (sms <= 0) return fail(VP_ERR_CUDA, "no CUDA device");

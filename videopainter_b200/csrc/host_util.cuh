@@ -7,6 +7,10 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
+#include <mutex>
+#include <unordered_map>
+
 #include "../../include/vp_b200.h"
 #include "common.cuh"
 
@@ -79,14 +83,34 @@ inline int make_tmap_bf16(CUtensorMap* map, const void* ptr, int rank, const uin
   return VP_OK;
 }
 
+// Per-device caches: the SM count and cudaFuncAttributeMaxDynamicSharedMemorySize are properties of (function, device), and a
+// process may drive several GPUs (one thread-local runtime per virtual rank: parallel.py).
+constexpr int kMaxDevices = 64;
+
 inline int sm_count() {
-  static int n = []() {
-    int dev = 0, v = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
-    return v;
-  }();
-  return n;
+  static std::atomic<int> cache[kMaxDevices];
+  int dev = 0, v = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 0;
+  v = cache[dev].load(std::memory_order_relaxed);
+  if (v > 0) return v;
+  if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+  cache[dev].store(v, std::memory_order_relaxed);
+  return v;
+}
+
+// Opt a kernel into `smem_bytes` of dynamic shared memory once per (kernel, device).
+inline int configure_once(const void* func, int smem_bytes) {
+  static std::mutex mu;
+  static std::unordered_map<const void*, unsigned long long> done;
+  int dev = 0;
+  VP_CHECK_CUDA(cudaGetDevice(&dev));
+  VP_REQUIRE(dev >= 0 && dev < kMaxDevices, VP_ERR_UNSUPPORTED, "device ordinal out of range");
+  std::lock_guard<std::mutex> g(mu);
+  unsigned long long& mask = done[func];
+  if ((mask >> dev) & 1ull) return VP_OK;
+  VP_CHECK_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  mask |= 1ull << dev;
+  return VP_OK;
 }
 
 }  // namespace vp

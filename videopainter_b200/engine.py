@@ -42,6 +42,9 @@ class Dims:
     freq_shift: float = 0.0
     resample: bool = False      # blocks built with CogVideoXAttnProcessor2_0_resample (T3D:98-99)
     is_branch: bool = False
+    wo_text: bool = False       # blocks built with CogVideoXAttnProcessor2_0_wo_text (T3D:96-97): video tokens only
+    fused_qkv: bool = False     # fuse_qkv_projections() (T3D:433-456): FusedCogVideoXAttnProcessor2_0 reads attn1.to_qkv and
+                                # takes neither the resample mask nor previous-window states (AP:2378-2436)
 
     @property
     def D(self) -> int:
@@ -82,36 +85,56 @@ class PackedModel:
 # ------------------------------------------------------------------------------------------------------------------
 # weight packing
 # ------------------------------------------------------------------------------------------------------------------
-def _linear_from_sd(sd: Dict[str, torch.Tensor], prefix: str, lora_scale: float = 1.0):
-    """Plain nn.Linear or a PEFT lora.Linear (base_layer + lora_A/lora_B per adapter); the adapter is merged:
-    W' = W + scale * B @ A with alpha == r at inference."""
+def _linear_from_sd(sd: Dict[str, torch.Tensor], prefix: str, lora_scale: float = 1.0,
+                    adapters: Optional[Dict[str, float]] = None):
+    """Plain nn.Linear or a PEFT lora.Linear (base_layer + lora_A/lora_B per adapter).  The adapters are merged the way
+    peft's lora.Linear.forward adds them (third-party, not vendored in the reference; published algorithm):
+        y = base(x) + sum over ACTIVE adapters a of  lora_B_a(lora_A_a(x)) * scaling[a]
+    with scaling[a] = lora_alpha / r (1.0 for the shipped adapter: the loader sets alpha = r, utils/peft_utils.py:153) times the
+    call's `attention_kwargs["scale"]` (scale_lora_layers, T3D:490-498)  =>  W' = W + sum_a scaling[a] * lora_scale * B_a @ A_a.
+    `adapters` = {adapter name: scaling[a]} of the ACTIVE adapters of this layer as read from the live module (models.py);
+    None (a bare state-dict) = every adapter found, scaling 1.0."""
     if prefix + ".weight" in sd:
         return sd[prefix + ".weight"], sd.get(prefix + ".bias")
     w = sd[prefix + ".base_layer.weight"].float()
     b = sd.get(prefix + ".base_layer.bias")
+    head = prefix + ".lora_A."
     for key in sd:
-        if key.startswith(prefix + ".lora_A.") and key.endswith(".weight"):
+        if key.startswith(head) and key.endswith(".weight"):
+            name = key[len(head):-len(".weight")]
+            if adapters is not None and name not in adapters:
+                continue
+            sc = lora_scale * (1.0 if adapters is None else adapters[name])
             a = sd[key].float()
             bb = sd[key.replace(".lora_A.", ".lora_B.")].float()
-            w = w + lora_scale * (bb.to(w.device) @ a.to(w.device))
+            w = w + sc * (bb.to(w.device) @ a.to(w.device))
     return w, b
 
 
-def pack_state_dict(sd: Dict[str, torch.Tensor], dims: Dims, device, lora_scale: float = 1.0) -> PackedModel:
+def pack_state_dict(sd: Dict[str, torch.Tensor], dims: Dims, device, lora_scale: float = 1.0,
+                    lora_adapters: Optional[Dict[str, Dict[str, float]]] = None) -> PackedModel:
+    """lora_adapters: {linear prefix: {active adapter: scaling}} from the live PEFT modules (None: see _linear_from_sd)."""
     def t(x):
         return None if x is None else x.detach().to(device=device, dtype=BF16).contiguous()
 
     def lin(prefix):
-        w, b = _linear_from_sd(sd, prefix, lora_scale)
+        ad = None if lora_adapters is None else lora_adapters.get(prefix, {})
+        w, b = _linear_from_sd(sd, prefix, lora_scale, ad)
         return t(w), t(b)
 
     D = dims.D
     blocks = []
     for i in range(dims.num_layers):
         p = f"transformer_blocks.{i}."
-        wq, bq = lin(p + "attn1.to_q")
-        wk, bk = lin(p + "attn1.to_k")
-        wv, bv = lin(p + "attn1.to_v")
+        if dims.fused_qkv:                                               # AP:2397: qkv = attn.to_qkv(hidden_states)
+            wqkv, bqkv = lin(p + "attn1.to_qkv")
+            if bqkv is None:
+                raise ValueError("attention projections without bias are not supported (CogVideoX uses attention_bias=True)")
+            (wq, wk, wv), (bq, bk, bv) = wqkv.chunk(3, dim=0), bqkv.chunk(3, dim=0)
+        else:
+            wq, bq = lin(p + "attn1.to_q")
+            wk, bk = lin(p + "attn1.to_k")
+            wv, bv = lin(p + "attn1.to_v")
         if bq is None or bk is None or bv is None:
             raise ValueError("attention projections without bias are not supported (CogVideoX uses attention_bias=True)")
         n1w, n1b = lin(p + "norm1.linear")
@@ -174,8 +197,9 @@ class _Workspace:
         self.xn = e(B * R, D)
         # peer mode: q, k, v, k2, v2 are the five slots of one buffer that the peers' QKV epilogues write into
         self.peer = rt is not None and rt.p2p and P > 1
+        self._shared = []
         if self.peer:
-            raw, self.ptrs_qkv = rt.alloc_shared(5 * Hl * S * 64 * 2, device)
+            raw, self.ptrs_qkv = self._share(rt, 5 * Hl * S * 64 * 2, device)
             self.qkv_sym = raw.view(BF16).view(5, Hl, S, 64)
             self.q, self.k, self.v, self.k2, self.v2 = (self.qkv_sym[i].unsqueeze(0) for i in range(5))
         else:
@@ -198,13 +222,51 @@ class _Workspace:
         self.xfull = None
         if self.peer:
             self.rt = rt
-            raw, self.ptrs_ao = rt.alloc_shared(P * R * Hl * 64 * 2, device)
+            raw, self.ptrs_ao = self._share(rt, P * R * Hl * 64 * 2, device)
             self.ao_recv = raw.view(BF16).view(P, R, Hl * 64)
-            self.flags, self.ptrs_flags = rt.alloc_shared(64, device)
+            self.flags, self.ptrs_flags = self._share(rt, 64, device)
             self.epoch = 0
+            # time-outs of the device barrier are counted in word PEER_ERR_WORD of the flag buffer; the count is copied to
+            # pinned host memory after every forward and looked at, without synchronising, before the next one
+            self.err_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+            self.err_event = None
+            self.err_seen = 0
             rt.ready()
         else:
             self.ao_recv = e(P, R, Hl * 64) if P > 1 else None
+
+    def _share(self, rt, nbytes, device):
+        t, ptrs = rt.alloc_shared(nbytes, device)
+        self._shared.append((t, ptrs))
+        return t, ptrs
+
+    def close(self):
+        """Release the peer-visible buffers of this workspace (IPC mappings of the peers, then the own allocations)."""
+        if self.peer:
+            self.rt.release_shared(self._shared)
+            self._shared = []
+            self.peer = False
+
+    def post_check(self):
+        if self.peer:
+            w = parallel.PEER_ERR_WORD
+            self.err_host.copy_(self.flags.view(torch.int32)[w:w + 1], non_blocking=True)
+            self.err_event = torch.cuda.Event()
+            self.err_event.record()
+
+    def poll_check(self, wait: bool = False):
+        """Raise if a device-side peer barrier of an earlier forward ran out of time (its results are invalid)."""
+        if not self.peer or self.err_event is None:
+            return
+        if wait:
+            self.err_event.synchronize()
+        if self.err_event.query():
+            n = int(self.err_host[0])
+            if n != self.err_seen:
+                self.err_seen = n
+                from ._lib import VpError
+                raise VpError(f"the device-side peer barrier timed out ({n} time-outs so far): a rank of the sequence-parallel "
+                              "group fell behind by more than VP_B200_PEER_TIMEOUT_MS; the affected step's results are invalid")
 
     def peer_sync(self):
         """All peer stores issued so far by every rank of the group are visible to every rank after this point of the
@@ -232,6 +294,8 @@ def _workspace(pm: PackedModel, B, S, Sv, sh: Shard, device, rt=None) -> _Worksp
     key = (B, S, Sv, sh.sp, sh.sp_rank, str(device), id(rt))
     ws = pm.workspace.get(key)
     if ws is None:
+        for old in pm.workspace.values():          # one shape at a time: a new shape releases the old buffers (peer memory too)
+            old.close()
         pm.workspace.clear()
         ws = _Workspace(pm, B, S, Sv, sh, device, rt)
         pm.workspace[key] = ws
@@ -283,6 +347,22 @@ def _embed_sharded(pm: PackedModel, ws: _Workspace, x_local: torch.Tensor, text,
         ws.xfull = torch.empty(B, St + Sv, pm.dims.D, dtype=BF16, device=ws.device)
     _embed(pm, ws, ws.xfull, text, src0, src1, B, Fr, H, W, St, Sv)
     x_local.copy_(ws.xfull[:, sh.row0:sh.row0 + sh.rows])
+
+
+def _embed_video_only(pm: PackedModel, ws: _Workspace, x_local: torch.Tensor, src0, src1, B, Fr, H, W, St, Sv):
+    """wo_text branch (BR:359-365 followed by BR:407-412): the patch embedding of the video tokens (+ their rows [St, St + Sv)
+    of the positional table); the text projection the reference also computes is dropped right away (BR:364) and never read."""
+    sh = ws.sh
+    x = x_local
+    if sh.sp > 1:
+        if ws.xfull is None:
+            ws.xfull = torch.empty(B, Sv, pm.dims.D, dtype=BF16, device=ws.device)
+        x = ws.xfull
+    ops.patchify(src0, src1, ws.patches, B * Fr, H, W, pm.kpad)
+    ops.gemm_gate_residual(ws.patches, pm.patch_w, pm.patch_b, x, B * Sv, pm.dims.D, pm.kpad, rows_per_batch=Sv, out_batch_rows=Sv,
+                           out_row_offset=0, res=pm.pos, res_batch_rows=0, res_row_offset=St)
+    if sh.sp > 1:
+        x_local.copy_(x[:, sh.row0:sh.row0 + sh.rows])
 
 
 def _qkv(pm, blk, ws, xn, which_first, rope, mask2=None, row_scale=None, masked_copy=False, group=None):
@@ -462,12 +542,18 @@ def _layout(pm: PackedModel, B_global: int, S: int, St: int):
 
 @torch.no_grad()
 def branch_forward(pm: PackedModel, hidden_states: torch.Tensor, encoder_hidden_states: torch.Tensor, branch_cond: torch.Tensor,
-                   timestep, image_rotary_emb, conditioning_scale: float = 1.0) -> List[torch.Tensor]:
-    """CogvideoXBranchModel.forward BR:295-434 (wo_text = False).  On several GPUs every rank is given the whole CFG batch and
-    returns the block samples of ITS sample and ITS video rows ([B_local, owned video rows, D]); transformer_forward on the
-    same rank consumes exactly that."""
+                   timestep, image_rotary_emb, conditioning_scale: float = 1.0, wo_text: bool = False) -> List[torch.Tensor]:
+    """CogvideoXBranchModel.forward BR:295-434.  wo_text = True (BR:407-412, T3D:186-216, AP:2316-2366): the blocks see the
+    video tokens only — same kernels with zero text rows (video expert of every LayerNormZero, RoPE on every row).  On several
+    GPUs every rank is given the whole CFG batch and returns the block samples of ITS sample and ITS video rows
+    ([B_local, owned video rows, D]); transformer_forward on the same rank consumes exactly that."""
     _check_inputs(pm, hidden_states, encoder_hidden_states)
     d = pm.dims
+    if bool(wo_text) != d.wo_text:
+        # the reference crashes here too: block.forward_wo_text needs the _wo_text processor (no encoder_hidden_states), and
+        # block.forward with that processor cannot unpack its single return value (T3D:149-167, AP:2316-2366)
+        raise ValueError("wo_text must match the attention processor the branch was built with "
+                         "(CogvideoXBranchModel(wo_text=True) <-> forward(wo_text=True))")
     dtype = hidden_states.dtype
     dev = hidden_states.device
     Bg, Fr, C, H, W = hidden_states.shape
@@ -475,20 +561,25 @@ def branch_forward(pm: PackedModel, hidden_states: torch.Tensor, encoder_hidden_
         raise ValueError(f"branch expects {d.patch_in_channels} conditioning channels, got {C} + {branch_cond.shape[2]}")
     Sv = Fr * (H // d.patch) * (W // d.patch)
     St = encoder_hidden_states.shape[1]
-    S = St + Sv
-    if pm.pos.shape[0] != S:
+    if pm.pos.shape[0] != St + Sv:
         raise ValueError("resolution / frame count must match the learned positional table (EMB:433-437)")
-    rt, bs, B, sh = _layout(pm, Bg, S, St)
+    S, St_seq = (Sv, 0) if d.wo_text else (St + Sv, St)              # rows the blocks run on / text rows among them
+    rt, bs, B, sh = _layout(pm, Bg, S, St_seq)
     group = rt                                                        # collectives of this rank (None on one GPU)
     if torch.is_tensor(timestep) and timestep.ndim > 0 and timestep.shape[0] == Bg:
         timestep = timestep[bs]
     ws = _workspace(pm, B, S, Sv, sh, dev, rt)
+    ws.poll_check()
     emb = _time_embedding(pm, timestep, B, dev)
     rope = _prep_rope(image_rotary_emb, dev, Sv, sh)
     R = sh.rows
     x = [torch.empty(B, R, d.D, dtype=BF16, device=dev) for _ in range(d.num_layers + 1)]
-    _embed_sharded(pm, ws, x[0], encoder_hidden_states[bs].to(BF16).contiguous(), hidden_states[bs].to(BF16).contiguous(),
-                   branch_cond[bs].to(BF16).contiguous(), B, Fr, H, W, St, Sv)
+    if d.wo_text:
+        _embed_video_only(pm, ws, x[0], hidden_states[bs].to(BF16).contiguous(), branch_cond[bs].to(BF16).contiguous(),
+                          B, Fr, H, W, St, Sv)
+    else:
+        _embed_sharded(pm, ws, x[0], encoder_hidden_states[bs].to(BF16).contiguous(), hidden_states[bs].to(BF16).contiguous(),
+                       branch_cond[bs].to(BF16).contiguous(), B, Fr, H, W, St, Sv)
     outs = []
     tab = _ada_tables(pm, emb)
     n6 = 6 * d.D
@@ -501,6 +592,7 @@ def branch_forward(pm: PackedModel, hidden_states: torch.Tensor, encoder_hidden_
         ops.gemm_bias(x[i + 1], pm.branch_w[i], pm.branch_b[i], o, B * R, d.D, d.D, rows_per_batch=R, out_batch_rows=sh.video_rows,
                       out_row_offset=-sh.text_rows, alpha=float(conditioning_scale))
         outs.append(o.to(dtype))
+    ws.post_check()
     return outs
 
 
@@ -535,6 +627,7 @@ def transformer_forward(pm: PackedModel, hidden_states: torch.Tensor, encoder_hi
     if torch.is_tensor(timestep) and timestep.ndim > 0 and timestep.shape[0] == Bg:
         timestep = timestep[bs]
     ws = _workspace(pm, B, S, Sv, sh, dev, rt)
+    ws.poll_check()
     emb = _time_embedding(pm, timestep, B, dev)
     rope = _prep_rope(image_rotary_emb, dev, Sv, sh)
 
@@ -562,6 +655,10 @@ def transformer_forward(pm: PackedModel, hidden_states: torch.Tensor, encoder_hi
     kw.pop("scale", None)      # LoRA scale: adapters are merged at pack time
     prev_states = kw.get("prev_hidden_states")
     prev_w = kw.get("prev_clip_weight")
+    if d.fused_qkv:        # FusedCogVideoXAttnProcessor2_0.__call__ has no prev_* parameters: Attention.forward drops them (AP:479-488)
+        prev_states = None
+    if d.wo_text:
+        raise ValueError("the backbone's blocks cannot use the wo_text processor (T3D:584 calls block.forward with text tokens)")
     prev_mask_f = None
     if prev_states is not None and d.resample and prev_w is not None and prev_w > 0.0:
         pmk = kw.get("prev_resample_mask")
@@ -640,4 +737,5 @@ def transformer_forward(pm: PackedModel, hidden_states: torch.Tensor, encoder_hi
         for b in range(Bg):
             ops.unpatchify(joint[b, St:], out[b], Fr, d.out_channels, H, W)
     hs_list = [xs[i + 1] for i in range(L)] if return_hidden_states else None
+    ws.post_check()
     return out.to(dtype), hs_list, resample_mask

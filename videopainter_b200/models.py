@@ -12,6 +12,7 @@ Neither has a CPU / eager fallback: a forward on a non-CUDA tensor raises.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Any, Dict, List, Optional, Tuple, Union
 
@@ -40,9 +41,10 @@ class _AdaLayerNorm(nn.Module):            # NRM:44-65
 
 
 class _Attention(nn.Module):               # AP:41-264 (the parts CogVideoX uses)
-    def __init__(self, dim, heads, head_dim, **fk):
+    def __init__(self, dim, heads, head_dim, processor=None, **fk):
         super().__init__()
         self.heads = heads
+        self.processor = processor             # AP:262-264; replaced by set_attn_processor / fuse_qkv_projections
         self.to_q = nn.Linear(dim, dim, **fk)
         self.to_k = nn.Linear(dim, dim, **fk)
         self.to_v = nn.Linear(dim, dim, **fk)
@@ -71,12 +73,25 @@ class CogVideoXAttnProcessor2_0_resample:
     pass
 
 
+class CogVideoXAttnProcessor2_0_wo_text:   # AP:2306-2366: video tokens only (branch built with wo_text=True)
+    pass
+
+
+class FusedCogVideoXAttnProcessor2_0:      # AP:2368-2436: one to_qkv projection; no resample mask, no previous-window states
+    pass
+
+
 class CogVideoXBlock(nn.Module):           # T3D:38-123
-    def __init__(self, dim, heads, head_dim, time_dim, eps, resample, **fk):
+    def __init__(self, dim, heads, head_dim, time_dim, eps, resample, wo_text=False, **fk):
         super().__init__()
         self.norm1 = _LayerNormZero(time_dim, dim, eps, **fk)
-        self.processor = CogVideoXAttnProcessor2_0_resample() if resample else CogVideoXAttnProcessor2_0()
-        self.attn1 = _Attention(dim, heads, head_dim, **fk)
+        if wo_text:                            # T3D:96-101
+            self.processor = CogVideoXAttnProcessor2_0_wo_text()
+        elif resample:
+            self.processor = CogVideoXAttnProcessor2_0_resample()
+        else:
+            self.processor = CogVideoXAttnProcessor2_0()
+        self.attn1 = _Attention(dim, heads, head_dim, processor=self.processor, **fk)
         self.norm2 = _LayerNormZero(time_dim, dim, eps, **fk)
         self.ff = _FeedForward(dim, **fk)
 
@@ -122,6 +137,29 @@ def _base(linear):
     return getattr(linear, "base_layer", linear)          # PEFT lora.Linear wraps the original module
 
 
+_PROC_MODES = {"CogVideoXAttnProcessor2_0": "plain", "CogVideoXAttnProcessor2_0_resample": "resample",
+               "CogVideoXAttnProcessor2_0_wo_text": "wo_text", "FusedCogVideoXAttnProcessor2_0": "fused"}
+
+
+def _processor_of(block):
+    """The processor that actually runs is attn1.processor (set_attn_processor / fuse_qkv_projections replace it, T3D:398-456);
+    block.processor only remembers what the block was constructed with (T3D:96-101)."""
+    proc = getattr(block.attn1, "processor", None)
+    return proc if proc is not None else getattr(block, "processor", None)
+
+
+def attn_mode(m: nn.Module) -> str:
+    modes = set()
+    for b in m.transformer_blocks:
+        name = type(_processor_of(b)).__name__
+        if name not in _PROC_MODES:
+            raise ValueError(f"attention processor {name} is not implemented on the B200 path (no fallback)")
+        modes.add(_PROC_MODES[name])
+    if len(modes) != 1:
+        raise ValueError(f"all blocks must use the same attention processor, found {sorted(modes)}")
+    return modes.pop()
+
+
 def dims_from_module(m: nn.Module, is_branch: bool) -> Dims:
     blocks = m.transformer_blocks                           # never config["num_layers"] (BR:265-269 mutates it)
     a0 = blocks[0].attn1
@@ -129,13 +167,34 @@ def dims_from_module(m: nn.Module, is_branch: bool) -> Dims:
     dim = _base(a0.to_q).out_features
     pe = m.patch_embed
     p = int(pe.patch_size)
+    mode = attn_mode(m)
     return Dims(heads=heads, head_dim=dim // heads, time_dim=m.time_embedding.linear_2.out_features,
                 text_dim=pe.text_proj.in_features, patch_in_channels=pe.proj.in_channels,
                 out_channels=m.proj_out.out_features // (p * p), patch=p, max_text=int(pe.max_text_seq_length),
                 num_layers=len(blocks), eps=float(m.norm_final.eps), flip_sin_to_cos=bool(m.time_proj.flip_sin_to_cos),
-                freq_shift=float(m.time_proj.downscale_freq_shift),
-                resample=type(blocks[0].processor).__name__ == "CogVideoXAttnProcessor2_0_resample",
-                is_branch=is_branch)
+                freq_shift=float(m.time_proj.downscale_freq_shift), resample=mode == "resample", is_branch=is_branch,
+                wo_text=mode == "wo_text", fused_qkv=mode == "fused")
+
+
+def lora_adapters(m: nn.Module) -> Dict[str, Dict[str, float]]:
+    """{linear prefix: {active adapter: scaling}} of every PEFT lora.Linear in `m` (duck-typed: base_layer + lora_A + lora_B),
+    following peft's lora.Linear.forward: disabled or merged layers add nothing on top of base_layer; otherwise every ACTIVE
+    adapter that has weights adds lora_B(lora_A(x)) * scaling[adapter]."""
+    out: Dict[str, Dict[str, float]] = {}
+    for name, mod in m.named_modules():
+        if not (hasattr(mod, "base_layer") and hasattr(mod, "lora_A") and hasattr(mod, "lora_B")):
+            continue
+        if bool(getattr(mod, "disable_adapters", False)) or bool(getattr(mod, "merged", False)):
+            out[name] = {}
+            continue
+        active = getattr(mod, "active_adapters", None)
+        if active is None:
+            active = list(mod.lora_A.keys())
+        if isinstance(active, str):
+            active = [active]
+        scaling = getattr(mod, "scaling", {}) or {}
+        out[name] = {a: float(scaling.get(a, 1.0)) for a in active if a in mod.lora_A}
+    return out
 
 
 def _fingerprint(m: nn.Module):
@@ -145,18 +204,58 @@ def _fingerprint(m: nn.Module):
     return (len(fp), hash(tuple(fp)))
 
 
-def packed_for(m: nn.Module, is_branch: bool, device) -> engine.PackedModel:
-    """Packed-weight cache keyed on (data_ptr, version) of every parameter: rebuilt after .to(), LoRA load, training."""
-    fp = (_fingerprint(m), str(device))
-    cached = getattr(m, "_vp_packed", None)
-    if cached is not None and cached[0] == fp:
-        return cached[1]
+def _sentinel_key(m: nn.Module, sentinels):
+    """Cheap steady-state identity of the packed weights: three sentinel parameters (first, middle, last: `.to()`,
+    `load_state_dict` and optimiser steps touch all of them) plus everything that changes WHAT is packed — the processor in
+    use and the PEFT state of the first attention projection (injection, set_adapters, disable, merge, scale).  The full
+    per-parameter fingerprint is only taken when this key changes (or always with VP_B200_STRICT_CACHE=1)."""
+    b0 = m.transformer_blocks[0]
+    lq = b0.attn1.to_q
+    lora_sig = (type(lq).__name__, tuple(sorted((getattr(lq, "scaling", None) or {}).items())),
+                tuple(getattr(lq, "active_adapters", None) or ()), bool(getattr(lq, "disable_adapters", False)),
+                bool(getattr(lq, "merged", False)))
+    return (tuple((p.data_ptr(), p._version) for p in sentinels), lora_sig, type(_processor_of(b0)).__name__,
+            len(m.transformer_blocks))
+
+
+_STRICT_CACHE = os.environ.get("VP_B200_STRICT_CACHE", "0") == "1"
+
+
+def packed_for(m: nn.Module, is_branch: bool, device, lora_scale: float = 1.0) -> engine.PackedModel:
+    """Packed-weight cache: rebuilt after .to(), load_state_dict, LoRA load / set_adapters / a different
+    attention_kwargs["scale"], processor changes (fuse_qkv_projections)."""
+    lora_scale = float(1.0 if lora_scale is None else lora_scale)
+    cached = m.__dict__.get("_vp_packed")
+    if cached is not None and not _STRICT_CACHE:
+        if cached["key"] == (_sentinel_key(m, cached["sentinels"]), str(device), lora_scale if cached["has_lora"] else 1.0):
+            return cached["pm"]
+    adapters = lora_adapters(m)
+    has_lora = any(adapters.values())
+    if not has_lora:
+        lora_scale = 1.0                                                    # scale_lora_layers finds no tuner layer: no effect
+    full = (_fingerprint(m), tuple(sorted((k, tuple(sorted(v.items()))) for k, v in adapters.items())), attn_mode(m),
+            str(device), lora_scale)
+    params = list(m.parameters())
+    sentinels = [params[0], params[len(params) // 2], params[-1]]
+    key = (_sentinel_key(m, sentinels), str(device), lora_scale)
+    if cached is not None and cached["full"] == full:
+        cached.update(key=key, sentinels=sentinels)
+        return cached["pm"]
     dims = dims_from_module(m, is_branch)
     if dims.head_dim != 64:
         raise ValueError("videopainter_b200 supports attention_head_dim == 64 (CogVideoX) only")
-    pm = engine.pack_state_dict(m.state_dict(), dims, device)
-    object.__setattr__(m, "_vp_packed", (fp, pm))
+    pm = engine.pack_state_dict(m.state_dict(), dims, device, lora_scale=lora_scale, lora_adapters=adapters)
+    if cached is not None:
+        for ws in cached["pm"].workspace.values():
+            ws.close()
+    object.__setattr__(m, "_vp_packed", {"key": key, "sentinels": sentinels, "full": full, "pm": pm, "has_lora": has_lora})
     return pm
+
+
+def invalidate(m: nn.Module) -> None:
+    """Drop the packed weights of `m` (needed only after in-place edits of single parameters that the sentinel check of
+    packed_for cannot see)."""
+    m.__dict__.pop("_vp_packed", None)
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -177,7 +276,8 @@ def transformer_forward(self, hidden_states: torch.Tensor, encoder_hidden_states
         raise NotImplementedError("timestep_cond is not used by any CogVideoX checkpoint (cond_proj is None, EMB:744-747)")
     if self_guidance_hidden_states is not None or self_guidance_masks is not None:
         raise NotImplementedError("self-guidance (T3D:593-594) is not used by the VideoPainter pipelines")
-    pm = packed_for(self, False, hidden_states.device)
+    lora_scale = (attention_kwargs or {}).get("scale", 1.0)     # T3D:490-498: scale_lora_layers(self, lora_scale)
+    pm = packed_for(self, False, hidden_states.device, lora_scale)
     out, hs, rmask = engine.transformer_forward(
         pm, hidden_states, encoder_hidden_states, timestep, image_rotary_emb, attention_kwargs, branch_block_samples,
         branch_block_masks, bool(add_first), bool(return_hidden_states), bool(return_resample_mask),
@@ -196,13 +296,12 @@ def branch_forward(self, hidden_states: torch.Tensor, encoder_hidden_states: tor
                    attention_kwargs: Optional[Dict[str, Any]] = None, mask_add: Optional[bool] = False,
                    wo_text: Optional[bool] = False, return_dict: bool = True):
     """Drop-in for CogvideoXBranchModel.forward (BR:295-434)."""
-    if wo_text:
-        raise NotImplementedError("wo_text branch (BR:407-412) is not enabled by any shipped script")
     if timestep_cond is not None:
         raise NotImplementedError("timestep_cond is not used by any CogVideoX checkpoint")
-    pm = packed_for(self, True, hidden_states.device)
+    lora_scale = (attention_kwargs or {}).get("scale", 1.0)     # BR:336-345
+    pm = packed_for(self, True, hidden_states.device, lora_scale)
     samples = engine.branch_forward(pm, hidden_states, encoder_hidden_states, branch_cond, timestep, image_rotary_emb,
-                                    conditioning_scale)
+                                    conditioning_scale, wo_text=bool(wo_text))
     samples = None if len(samples) == 0 else samples
     if not return_dict:
         return (samples,)
@@ -220,7 +319,7 @@ class _Base(nn.Module):
     def _build(self, is_branch: bool, num_attention_heads, attention_head_dim, in_channels, out_channels, flip_sin_to_cos,
                freq_shift, time_embed_dim, text_embed_dim, num_layers, sample_width, sample_height, sample_frames,
                patch_size, temporal_compression_ratio, max_text_seq_length, norm_eps, use_rotary_positional_embeddings,
-               use_learned_positional_embeddings, id_pool_resample_learnable, fk):
+               use_learned_positional_embeddings, id_pool_resample_learnable, fk, wo_text=False):
         if not (use_rotary_positional_embeddings and use_learned_positional_embeddings):
             raise ValueError("only rotary + learned positional embeddings (CogVideoX-5B-I2V) are supported")
         dim = num_attention_heads * attention_head_dim
@@ -234,13 +333,31 @@ class _Base(nn.Module):
         self.time_embedding = _TimestepEmbedding(dim, time_embed_dim, **fk)
         self.transformer_blocks = nn.ModuleList([
             CogVideoXBlock(dim, num_attention_heads, attention_head_dim, time_embed_dim, norm_eps,
-                           id_pool_resample_learnable and not is_branch, **fk) for _ in range(num_layers)])
+                           id_pool_resample_learnable and not is_branch, wo_text=wo_text, **fk) for _ in range(num_layers)])
         self.norm_final = nn.LayerNorm(dim, norm_eps, **fk)
         self.norm_out = _AdaLayerNorm(time_embed_dim, dim, norm_eps, **fk)
         self.proj_out = nn.Linear(dim, patch_size * patch_size * out_channels, **fk)
         if is_branch:
             self.branch_blocks = nn.ModuleList([nn.Linear(dim, dim, **fk) for _ in range(num_layers)])
             self.branch_x_embedder = nn.Linear(in_channels, dim, **fk)
+
+    @torch.no_grad()
+    def fuse_qkv_projections(self):
+        """T3D:433-456 / AP:665-712: one `to_qkv` Linear per attention (a copy of [Wq; Wk; Wv]) and the fused processor."""
+        self.original_attn_processors = [b.attn1.processor for b in self.transformer_blocks]
+        for b in self.transformer_blocks:
+            a = b.attn1
+            w = torch.cat([a.to_q.weight.data, a.to_k.weight.data, a.to_v.weight.data])
+            a.to_qkv = nn.Linear(w.shape[1], w.shape[0], bias=True, device=w.device, dtype=w.dtype)
+            a.to_qkv.weight.copy_(w)
+            a.to_qkv.bias.copy_(torch.cat([a.to_q.bias.data, a.to_k.bias.data, a.to_v.bias.data]))
+            a.processor = FusedCogVideoXAttnProcessor2_0()
+
+    def unfuse_qkv_projections(self):
+        """T3D:458-470."""
+        if getattr(self, "original_attn_processors", None) is not None:
+            for b, proc in zip(self.transformer_blocks, self.original_attn_processors):
+                b.attn1.processor = proc
 
 
 class CogVideoXTransformer3DModel(_Base):
@@ -283,13 +400,11 @@ class CogvideoXBranchModel(_Base):
                  use_learned_positional_embeddings: bool = False, wo_text: bool = False,
                  id_pool_resample_learnable: bool = False, device=None, dtype=None):
         super().__init__()
-        if wo_text:
-            raise ValueError("wo_text branches are not supported")
         fk = dict(device=device, dtype=dtype)
         self._build(True, num_attention_heads, attention_head_dim, in_channels, out_channels, flip_sin_to_cos, freq_shift,
                     time_embed_dim, text_embed_dim, num_layers, sample_width, sample_height, sample_frames, patch_size,
                     temporal_compression_ratio, max_text_seq_length, norm_eps, use_rotary_positional_embeddings,
-                    use_learned_positional_embeddings, False, fk)
+                    use_learned_positional_embeddings, False, fk, wo_text=bool(wo_text))
 
     forward = branch_forward
 

@@ -1,15 +1,57 @@
 """Torch-tensor front ends of the C ABI (include/vp_b200.h).  PyTorch supplies device memory and the current stream;
 every computation happens in libvp_b200.so.  All functions raise if a tensor is not a contiguous CUDA tensor of the
-expected dtype — there is no fallback path."""
+expected dtype — there is no fallback path.
+
+The launches go through `torch.ops.vp_b200.*` (csrc/torch_ops.cpp: TORCH_LIBRARY thin wrappers around the C ABI, SURVEY.md
+§8b): same arguments as the C prototypes in the same order, tensors instead of pointers, no `stream` (the wrapper passes the
+current CUDA stream).  Host-side utilities without a stream (peer-memory allocation) are called through ctypes (_lib.py), and
+so is everything when VP_B200_LIB selects a differently-tuned development build of the library."""
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
 
+from . import _lib
 from ._lib import check, lib
 
 BF16 = torch.bfloat16
+
+_torch_ns = None     # torch.ops.vp_b200 once loaded
+
+
+def _ns():
+    global _torch_ns
+    if _torch_ns is None:
+        from .build import TORCH_LIB
+        if not os.path.exists(TORCH_LIB):
+            raise RuntimeError(f"{TORCH_LIB} is missing: build it with `python -m videopainter_b200.build` (there is no CPU or "
+                               "PyTorch fallback for the denoising path)")
+        lib()                                        # fail loudly if libvp_b200.so itself is missing
+        torch.ops.load_library(TORCH_LIB)
+        _torch_ns = torch.ops.vp_b200
+    return _torch_ns
+
+
+_VIA_CTYPES = "VP_B200_LIB" in os.environ            # development builds are only reachable through ctypes
+
+
+def _launch(name: str, *args) -> None:
+    """One kernel launch: `args` are the C arguments of vp_<name> without the trailing stream — tensors (or None) where
+    the prototype has a device pointer, lists of device addresses where it has a pointer array, ints and floats otherwise."""
+    if not _VIA_CTYPES:
+        getattr(_ns(), name)(*args)
+        return
+    conv = []
+    for a in args:
+        if torch.is_tensor(a):
+            conv.append(a.data_ptr())
+        elif isinstance(a, (list, tuple)):
+            conv.append(_ptr_array(a))
+        else:
+            conv.append(a)
+    check(getattr(lib(), "vp_" + name)(*conv, _stream()), "vp_" + name)
 
 # ---- optional per-op device timing (bench.py): CUDA events on the launching stream around every C-ABI call ----------
 _prof = None          # None, or dict name -> list[(start_event, end_event, work)]
@@ -59,16 +101,16 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
-def _base(t: Optional[torch.Tensor], dtype=BF16) -> Optional[int]:
-    """Base address of a CUDA tensor that the kernel indexes with its own strides (views into larger buffers)."""
+def _base(t: Optional[torch.Tensor], dtype=BF16) -> Optional[torch.Tensor]:
+    """A CUDA tensor that the kernel indexes with its own strides (views into larger buffers): only its base address counts."""
     if t is None:
         return None
     if not t.is_cuda or t.dtype != dtype:
         raise RuntimeError(f"expected a CUDA {dtype} tensor (the B200 path has no CPU fallback)")
-    return t.data_ptr()
+    return t
 
 
-def _p(t: Optional[torch.Tensor], dtype=None, name: str = "tensor") -> Optional[int]:
+def _p(t: Optional[torch.Tensor], dtype=None, name: str = "tensor") -> Optional[torch.Tensor]:
     if t is None:
         return None
     if not t.is_cuda:
@@ -77,7 +119,7 @@ def _p(t: Optional[torch.Tensor], dtype=None, name: str = "tensor") -> Optional[
         raise RuntimeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
     if not t.is_contiguous():
         raise RuntimeError(f"{name}: expected a contiguous tensor")
-    return t.data_ptr()
+    return t
 
 
 @_timed('time_sinusoid')
@@ -89,7 +131,7 @@ def time_sinusoid(timestep: torch.Tensor, dim: int, flip_sin_to_cos: bool, freq_
     else:
         timestep = timestep.to(torch.float32).contiguous()
         ti, tf = None, _p(timestep, torch.float32, "timestep")
-    check(lib().vp_time_sinusoid(ti, tf, _p(out), B, dim, int(flip_sin_to_cos), float(freq_shift), _stream()), "vp_time_sinusoid")
+    _launch("time_sinusoid", ti, tf, _p(out), B, dim, int(flip_sin_to_cos), float(freq_shift))
     return out
 
 
@@ -100,8 +142,8 @@ def gemv(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], ac
     N = weight.shape[0]
     if out is None:
         out = torch.empty(B, N, dtype=torch.float32, device=x.device)
-    check(lib().vp_gemv(_p(x, torch.float32, "gemv.in"), _p(weight, BF16, "gemv.weight"), _p(bias, BF16, "gemv.bias"),
-                        _p(out, torch.float32, "gemv.out"), B, N, K, int(act_silu), _stream()), "vp_gemv")
+    _launch("gemv", _p(x, torch.float32, "gemv.in"), _p(weight, BF16, "gemv.weight"), _p(bias, BF16, "gemv.bias"),
+                        _p(out, torch.float32, "gemv.out"), B, N, K, int(act_silu))
     return out
 
 
@@ -109,33 +151,33 @@ def gemv(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], ac
 def ln_modulate(x: torch.Tensor, x_batch_rows: int, x_row_offset: int, y: torch.Tensor, batch: int, rows_per_batch: int,
                 dim: int, gamma, beta, eps: float, mod: Optional[torch.Tensor], offs=(0, 0, 0, 0), text_len: int = 0):
     """offs = (shift_video, scale_video, shift_text, scale_text) element offsets into one batch row of `mod`."""
-    check(lib().vp_ln_modulate(_p(x, BF16, "ln.x"), x_batch_rows, x_row_offset, _p(y, BF16, "ln.y"), batch, rows_per_batch, dim,
+    _launch("ln_modulate", _p(x, BF16, "ln.x"), x_batch_rows, x_row_offset, _p(y, BF16, "ln.y"), batch, rows_per_batch, dim,
                                _p(gamma, BF16, "ln.gamma"), _p(beta, BF16, "ln.beta"), float(eps),
                                _base(mod, torch.float32), 0 if mod is None else mod.stride(0),
-                               offs[0], offs[1], offs[2], offs[3], text_len, _stream()), "vp_ln_modulate")
+                               offs[0], offs[1], offs[2], offs[3], text_len)
     return y
 
 
 @_timed('ln_final')
 def ln_final(x, x_batch_rows, x_row_offset, y, batch, rows_per_batch, dim, g1, b1, g2, b2, eps, mod, shift_off, scale_off):
-    check(lib().vp_ln_final(_p(x, BF16, "lnf.x"), x_batch_rows, x_row_offset, _p(y, BF16, "lnf.y"), batch, rows_per_batch, dim,
+    _launch("ln_final", _p(x, BF16, "lnf.x"), x_batch_rows, x_row_offset, _p(y, BF16, "lnf.y"), batch, rows_per_batch, dim,
                             _p(g1, BF16), _p(b1, BF16), _p(g2, BF16), _p(b2, BF16), float(eps),
-                            _p(mod, torch.float32, "lnf.mod"), mod.shape[1], shift_off, scale_off, _stream()), "vp_ln_final")
+                            _p(mod, torch.float32, "lnf.mod"), mod.shape[1], shift_off, scale_off)
     return y
 
 
 @_timed('gemm_bias', _gemm_flops)
 def gemm_bias(a, w, bias, out, m, n, k, rows_per_batch, out_batch_rows, out_row_offset, alpha=1.0, lda=None, ldw=None, ldo=None):
-    check(lib().vp_gemm_bias(_p(a, BF16, "gemm.a"), lda or k, _p(w, BF16, "gemm.w"), ldw or k, _p(bias, BF16, "gemm.bias"),
+    _launch("gemm_bias", _p(a, BF16, "gemm.a"), lda or k, _p(w, BF16, "gemm.w"), ldw or k, _p(bias, BF16, "gemm.bias"),
                              _p(out, BF16, "gemm.out"), ldo or n, m, n, k, rows_per_batch, out_batch_rows, out_row_offset,
-                             float(alpha), _stream()), "vp_gemm_bias")
+                             float(alpha))
     return out
 
 
 @_timed('gemm_gelu', _gemm_flops)
 def gemm_gelu(a, w, bias, out, m, n, k):
-    check(lib().vp_gemm_gelu(_p(a, BF16, "gemm.a"), k, _p(w, BF16, "gemm.w"), k, _p(bias, BF16, "gemm.bias"),
-                             _p(out, BF16, "gemm.out"), n, m, n, k, _stream()), "vp_gemm_gelu")
+    _launch("gemm_gelu", _p(a, BF16, "gemm.a"), k, _p(w, BF16, "gemm.w"), k, _p(bias, BF16, "gemm.bias"),
+                             _p(out, BF16, "gemm.out"), n, m, n, k)
     return out
 
 
@@ -144,13 +186,12 @@ def gemm_gate_residual(a, w, bias, out, m, n, k, rows_per_batch, out_batch_rows,
                        res_row_offset, gate=None, gate_video_off=0, gate_text_off=0, text_len=0, inject=None,
                        inject_batch_stride=0, ldi=0, inject_mask=None, video_len=0, lda=None, ldw=None, a_k_chunk=0,
                        a_chunk_stride=0):
-    check(lib().vp_gemm_gate_residual(
+    _launch("gemm_gate_residual", 
         _p(a, BF16, "gemm.a"), lda or k, _p(w, BF16, "gemm.w"), ldw or k, _p(bias, BF16, "gemm.bias"), _p(out, BF16, "gemm.out"),
         n, m, n, k, rows_per_batch, out_batch_rows, out_row_offset, _p(res, BF16, "gemm.res"), n, res_batch_rows, res_row_offset,
         _base(gate, torch.float32), 0 if gate is None else gate.stride(0), gate_video_off, gate_text_off, text_len,
-        None if inject is None else inject.data_ptr(), inject_batch_stride, ldi,
-        _p(inject_mask, torch.uint8, "gemm.inject_mask"), video_len, a_k_chunk, a_chunk_stride, _stream()),
-        "vp_gemm_gate_residual")
+        _base(inject), inject_batch_stride, ldi,
+        _p(inject_mask, torch.uint8, "gemm.inject_mask"), video_len, a_k_chunk, a_chunk_stride)
     return out
 
 
@@ -160,13 +201,13 @@ def gemm_qkv(a, w, bias, m, k, batch_rows, heads, qkv_first, q_out, k_out, v_out
     """heads_per_dest / dest_stride: Ulysses send layout (include/vp_b200.h); q_out .. v2_out may then be views into one send
     buffer, so only their base addresses are taken."""
     cos, sin, cs = _rope3(rope)
-    check(lib().vp_gemm_qkv(
-        _p(a, BF16, "qkv.a"), k, _p(w, BF16, "qkv.w") if w.is_contiguous() else w.data_ptr(), ldw or k, _p(bias, BF16, "qkv.bias"),
+    _launch("gemm_qkv", 
+        _p(a, BF16, "qkv.a"), k, _base(w), ldw or k, _p(bias, BF16, "qkv.bias"),
         m, k, batch_rows, heads, qkv_first, _base(q_out), _base(k_out), _base(v_out), _base(k2_out), _base(v2_out),
         _p(mask2, torch.uint8, "qkv.mask2"), _p(row_scale, torch.float32, "qkv.row_scale"),
         _p(norm_q[0], BF16) if norm_q else None, _p(norm_q[1], BF16) if norm_q else None, _p(norm_k[0], BF16), _p(norm_k[1], BF16),
         float(qk_eps), _base(cos, torch.float32), _base(sin, torch.float32), _base(cs, torch.float32), text_len,
-        heads_per_dest or heads, dest_stride, _stream()), "vp_gemm_qkv")
+        heads_per_dest or heads, dest_stride)
 
 
 def _rope3(rope):
@@ -189,49 +230,47 @@ def gemm_qkv_peer(a, w, bias, m, k, heads, qkv_first, q_out, k_out, v_out, norm_
     """QKV GEMM whose epilogue stores each head into its destination rank's attention buffer over peer memory
     (include/vp_b200.h vp_gemm_qkv_peer).  peer_ptrs: data pointers of every rank's buffer, by rank."""
     cos, sin, cs = _rope3(rope)
-    check(lib().vp_gemm_qkv_peer(
-        _p(a, BF16, "qkv.a"), k, _p(w, BF16, "qkv.w") if w.is_contiguous() else w.data_ptr(), ldw or k, _p(bias, BF16, "qkv.bias"),
+    _launch("gemm_qkv_peer", 
+        _p(a, BF16, "qkv.a"), k, _base(w), ldw or k, _p(bias, BF16, "qkv.bias"),
         m, k, heads, qkv_first, _base(q_out), _base(k_out), _base(v_out), _base(k2_out), _base(v2_out),
         _p(mask2, torch.uint8, "qkv.mask2"), _p(row_scale, torch.float32, "qkv.row_scale"),
         _p(norm_q[0], BF16) if norm_q else None, _p(norm_q[1], BF16) if norm_q else None, _p(norm_k[0], BF16), _p(norm_k[1], BF16),
         float(qk_eps), _base(cos, torch.float32), _base(sin, torch.float32), _base(cs, torch.float32), text_len,
-        _ptr_array(peer_ptrs), len(peer_ptrs),
-        _base(local_base), seq_total, row_offset, _stream()), "vp_gemm_qkv_peer")
+        list(peer_ptrs), len(peer_ptrs),
+        _base(local_base), seq_total, row_offset)
 
 
 @_timed('attention', lambda q, k0, v0, peer_ptrs, my_rank, ldo, heads, seq_q, kv_len0, scale, k1=None, v1=None, kv_len1=0, **kw: 4.0 * heads * seq_q * (kv_len0 + kv_len1) * 64)
 def attention_peer(q, k0, v0, peer_ptrs, my_rank, ldo, heads, seq_q, kv_len0, softmax_scale, k1=None, v1=None, kv_len1=0,
                    out_scale=1.0):
-    check(lib().vp_attention_peer(_p(q, BF16, "attn.q"), _p(k0, BF16, "attn.k"), _p(v0, BF16, "attn.v"), kv_len0, _p(k1, BF16),
-                                  _p(v1, BF16), kv_len1, _ptr_array(peer_ptrs), len(peer_ptrs), my_rank, ldo, heads, seq_q,
-                                  float(softmax_scale), float(out_scale), _stream()), "vp_attention_peer")
+    _launch("attention_peer", _p(q, BF16, "attn.q"), _p(k0, BF16, "attn.k"), _p(v0, BF16, "attn.v"), kv_len0, _p(k1, BF16),
+                                  _p(v1, BF16), kv_len1, list(peer_ptrs), len(peer_ptrs), my_rank, ldo, heads, seq_q,
+                                  float(softmax_scale), float(out_scale))
 
 
 @_timed('peer_scatter')
 def peer_scatter(src, peer_ptrs, my_rank, bytes_per_peer):
-    check(lib().vp_peer_scatter(_p(src, name="scatter.src"), _ptr_array(peer_ptrs), len(peer_ptrs), my_rank, bytes_per_peer, _stream()),
-          "vp_peer_scatter")
+    _launch("peer_scatter", _p(src, name="scatter.src"), list(peer_ptrs), len(peer_ptrs), my_rank, bytes_per_peer)
 
 
 @_timed('peer_barrier')
 def peer_barrier(flag_ptrs, my_rank, epoch):
-    check(lib().vp_peer_barrier(_ptr_array(flag_ptrs), len(flag_ptrs), my_rank, epoch & 0xffffffff, _stream()), "vp_peer_barrier")
+    _launch("peer_barrier", list(flag_ptrs), len(flag_ptrs), my_rank, epoch & 0xffffffff)
 
 
 @_timed('a2a_unpack', lambda src, dsts, peers, heads_local, rows_per_peer: 4.0 * len(dsts) * peers * heads_local * rows_per_peer * 64)
 def a2a_unpack_heads(src, dsts, peers, heads_local, rows_per_peer):
     """src [peers][len(dsts)][heads_local][rows_per_peer][64] -> dsts[i] [heads_local][peers * rows_per_peer][64]."""
     ptrs = [_p(d, BF16, "unpack.dst") for d in dsts] + [None] * (5 - len(dsts))
-    check(lib().vp_a2a_unpack_heads(_p(src, BF16, "unpack.src"), *ptrs, len(dsts), peers, heads_local, rows_per_peer, _stream()),
-          "vp_a2a_unpack_heads")
+    _launch("a2a_unpack_heads", _p(src, BF16, "unpack.src"), *ptrs, len(dsts), peers, heads_local, rows_per_peer)
 
 
 @_timed('attention', lambda q, k0, v0, out, batch, heads, seq_q, kv_len0, scale, k1=None, v1=None, kv_len1=0, **kw: 4.0 * batch * heads * seq_q * (kv_len0 + kv_len1) * 64)
 def attention(q, k0, v0, out, batch, heads, seq_q, kv_len0, softmax_scale, k1=None, v1=None, kv_len1=0, out_scale=1.0,
               accumulate=False, ldo=None):
-    check(lib().vp_attention(_p(q, BF16, "attn.q"), _p(k0, BF16, "attn.k"), _p(v0, BF16, "attn.v"), kv_len0, _p(k1, BF16), _p(v1, BF16),
+    _launch("attention", _p(q, BF16, "attn.q"), _p(k0, BF16, "attn.k"), _p(v0, BF16, "attn.v"), kv_len0, _p(k1, BF16), _p(v1, BF16),
                              kv_len1, _p(out, BF16, "attn.out"), ldo or heads * 64, batch, heads, seq_q, float(softmax_scale),
-                             float(out_scale), int(accumulate), _stream()), "vp_attention")
+                             float(out_scale), int(accumulate))
     return out
 
 
@@ -239,20 +278,19 @@ def attention(q, k0, v0, out, batch, heads, seq_q, kv_len0, softmax_scale, k1=No
 def patchify(src0, src1, out, bf, h, w, kpad):
     c0 = src0.shape[-3]
     c1 = 0 if src1 is None else src1.shape[-3]
-    check(lib().vp_patchify(_p(src0, BF16, "patchify.src0"), c0, _p(src1, BF16, "patchify.src1"), c1, bf, h, w, _p(out, BF16), kpad,
-                            _stream()), "vp_patchify")
+    _launch("patchify", _p(src0, BF16, "patchify.src0"), c0, _p(src1, BF16, "patchify.src1"), c1, bf, h, w, _p(out, BF16), kpad)
     return out
 
 
 @_timed('mask_pool')
 def mask_pool(mask, out, bf, h, w):
-    check(lib().vp_mask_pool(_p(mask, BF16, "mask"), bf, h, w, _p(out, torch.uint8), _stream()), "vp_mask_pool")
+    _launch("mask_pool", _p(mask, BF16, "mask"), bf, h, w, _p(out, torch.uint8))
     return out
 
 
 @_timed('unpatchify')
 def unpatchify(proj, out, bf, c, h, w):
-    check(lib().vp_unpatchify(_p(proj, BF16, "unpatchify.proj"), bf, c, h, w, _p(out, BF16), _stream()), "vp_unpatchify")
+    _launch("unpatchify", _p(proj, BF16, "unpatchify.proj"), bf, c, h, w, _p(out, BF16))
     return out
 
 
@@ -278,6 +316,17 @@ class PeerBuffer:
             self.tensor = None
             check(lib().vp_peer_free(self.ptr), "vp_peer_free")
             self.ptr = None
+
+
+def peer_close(ptr: int) -> None:
+    """Unmap a peer buffer opened with peer_open."""
+    check(lib().vp_peer_close(ptr), "vp_peer_close")
+
+
+def peer_set_timeout_ms(ms: int) -> None:
+    """Bound of the device-side peer barrier's wait (0 = wait for ever).  A barrier that runs out of time adds one to word 8
+    of the rank's flag buffer and lets the stream continue; it never traps."""
+    check(lib().vp_peer_set_timeout_ms(int(ms)), "vp_peer_set_timeout_ms")
 
 
 def peer_open(handle: bytes, device) -> int:

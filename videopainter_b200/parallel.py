@@ -115,7 +115,7 @@ class Runtime:
         # p2p: fuse the Ulysses all-to-alls into the producing kernels' epilogues as stores into peer memory (NVLink);
         # VP_B200_P2P=0 keeps the NCCL all-to-all path
         self.p2p = (os.environ.get("VP_B200_P2P", "1") != "0") if p2p is None else p2p
-        self._keep = []            # peer storages opened through CUDA IPC must outlive the pointers handed out
+        self._shared = {}          # own PeerBuffer + the peers' IPC mappings, by local data pointer (released by release_shared)
 
     def shard(self, seq: int, text: int, heads: int) -> Shard:
         return Shard(self.plan.sp, self.plan.sp_rank, seq, text, heads)
@@ -149,8 +149,29 @@ class Runtime:
         if any(h is None for h in handles):
             raise RuntimeError(f"peer-visible allocation failed on a rank of the group ({err})")
         ptrs = [buf.ptr if r == self.plan.sp_rank else ops.peer_open(h, device) for r, h in enumerate(handles)]
-        self._keep.append(buf)
+        self._shared[buf.ptr] = (buf, ptrs)
         return buf.tensor, ptrs
+
+    def release_shared(self, allocations) -> None:
+        """Collective over the sequence-parallel group: undo alloc_shared for the given (tensor, ptrs) pairs — every rank first
+        unmaps its peers' buffers, then (after a group barrier: nobody maps them any more) frees its own."""
+        import torch
+        import torch.distributed as dist
+        from . import ops
+        torch.cuda.synchronize()
+        mine = []
+        for t, _ in allocations:
+            rec = self._shared.pop(t.data_ptr(), None)
+            if rec is None:
+                continue
+            buf, ptrs = rec
+            for r, ptr in enumerate(ptrs):
+                if r != self.plan.sp_rank:
+                    ops.peer_close(ptr)
+            mine.append(buf)
+        dist.barrier(group=self.sp_group)
+        for buf in mine:
+            buf.free()
 
     def ready(self) -> None:
         """Collective: everything the ranks did to the shared buffers so far (zeroing the flags) is complete everywhere."""
@@ -169,6 +190,8 @@ class Runtime:
         from . import ops
         ops.peer_barrier(flag_ptrs, self.plan.sp_rank, epoch)
 
+
+PEER_ERR_WORD = 8             # 32-bit word of a rank's 64-byte flag buffer that counts device-barrier time-outs (elementwise.cu)
 
 _tls = threading.local()      # per thread, so that tests can run several virtual ranks of one process side by side
 
@@ -195,24 +218,71 @@ def init(world: Optional[int] = None, rank: Optional[int] = None) -> Runtime:
 
 
 def _probe_peer_memory(rt: Runtime) -> bool:
-    """Collective: can every rank of every sequence-parallel group map its peers' memory (CUDA IPC + peer access)?  All
-    ranks get the same answer; on False the data path uses the NCCL all-to-all instead (same kernels, same results)."""
+    """Collective: can every rank of every sequence-parallel group map its peers' memory (CUDA IPC + peer access), store
+    into it and pass the device-side barrier?  All ranks get the same answer; on False the data path uses the NCCL
+    all-to-all instead (same kernels, same results).  A failure on ONE rank must not leave the others in a group barrier:
+    every step that can fail locally is followed by a world-wide agreement (all_reduce MIN) before the next collective."""
+    import warnings
+
     import torch
     import torch.distributed as dist
-    ok = 1
-    try:
-        dev = torch.device("cuda", torch.cuda.current_device())
-        t, ptrs = rt.alloc_shared(256, dev)
-        t.fill_(1)
-        rt.ready()
-        ok = int(all(p for p in ptrs))
-    except Exception as e:   # noqa: BLE001 - any failure means "no peer memory here"
-        import warnings
-        warnings.warn(f"videopainter_b200: peer memory unavailable ({e}); using the NCCL all-to-all path")
-        ok = 0
-    flag = torch.tensor([ok], device="cuda")
-    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-    return bool(flag.item())
+    from . import ops
+
+    def agree(ok: bool) -> bool:
+        flag = torch.tensor([1 if ok else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        return bool(flag.item())
+
+    dev = torch.device("cuda", torch.cuda.current_device())
+    P, me = rt.plan.sp, rt.plan.sp_rank
+    bufs, why = [], None
+    try:                                                        # 1. local allocations (data [P][16 B], flags 64 B)
+        bufs = [ops.PeerBuffer(16 * P, dev), ops.PeerBuffer(64, dev)]
+    except Exception as e:   # noqa: BLE001
+        why = e
+    handles = [None] * P                                        # 2. exchange the handles (collective, cannot fail locally)
+    dist.all_gather_object(handles, None if why else [b.handle for b in bufs], group=rt.sp_group)
+    ptrs = [[], []]
+    if why is None and all(h is not None for h in handles):     # 3. map the peers' buffers
+        try:
+            for i in range(2):
+                ptrs[i] = [bufs[i].ptr if r == me else ops.peer_open(handles[r][i], dev) for r in range(P)]
+        except Exception as e:   # noqa: BLE001
+            why = e
+    elif why is None:
+        why = RuntimeError("a peer could not allocate")
+    ok = agree(why is None)
+    if ok:                                                      # 4. the real thing: peer stores, device barrier, check
+        try:
+            torch.cuda.synchronize()
+            dist.barrier(group=rt.sp_group)                     # zero fill of every rank's buffers has completed
+            src = torch.full((P, 16), me + 1, dtype=torch.uint8, device=dev)
+            ops.peer_scatter(src, ptrs[0], me, 16)
+            ops.peer_barrier(ptrs[1], me, 1)
+            got = bufs[0].tensor.view(P, 16)[:, 0].cpu().tolist()
+            errs = int(bufs[1].tensor.view(torch.int32)[PEER_ERR_WORD])
+            if got != list(range(1, P + 1)) or errs:
+                why = RuntimeError(f"peer stores not visible (slots {got}, barrier time-outs {errs})")
+        except Exception as e:   # noqa: BLE001
+            why = e
+        ok = agree(why is None)
+    try:                                                        # 5. release (mappings first, own memory after a barrier)
+        torch.cuda.synchronize()
+        for i in range(2):
+            for r, ptr in enumerate(ptrs[i]):
+                if r != me:
+                    ops.peer_close(ptr)
+    except Exception:   # noqa: BLE001
+        pass
+    dist.barrier(group=rt.sp_group)
+    for b in bufs:
+        try:
+            b.free()
+        except Exception:   # noqa: BLE001
+            pass
+    if not ok and why is not None:
+        warnings.warn(f"videopainter_b200: peer memory unavailable ({why}); using the NCCL all-to-all path")
+    return ok
 
 
 def install(rt: Optional[Runtime]) -> Optional[Runtime]:

@@ -18,7 +18,6 @@ from typing import List, Optional, Sequence
 import torch
 
 from . import ops
-from ._lib import check, lib
 
 BF16 = torch.bfloat16
 
@@ -113,10 +112,10 @@ class StepEnd:
         out = torch.empty_like(latents)
         sa, sb, renoise = self.renoise_coefficients(i)
         p = ops._p
-        check(lib().vp_step_end(p(noise_pred, BF16, "noise_pred"), float(self.guidance(i)), p(latents, BF16, "latents"),
-                                p(old_pred, torch.float32, "old_pred") if second else None, p(noise, BF16, "noise"), *co[:-1], second,
-                                p(pred), p(prev), p(out), p(gt, BF16, "gt"), p(noise0, BF16, "noise0") if gt is not None else None,
-                                p(mask, BF16, "mask") if gt is not None else None, C, H * W, sa, sb, renoise, int(self.mask_background),
-                                n, ops._stream()), "vp_step_end")
+        ops._launch("step_end", p(noise_pred, BF16, "noise_pred"), float(self.guidance(i)), p(latents, BF16, "latents"),
+                    p(old_pred, torch.float32, "old_pred") if second else None, p(noise, BF16, "noise"),
+                    *[float(c) for c in co[:-1]], int(second), p(pred), p(prev), p(out), p(gt, BF16, "gt"),
+                    p(noise0, BF16, "noise0") if gt is not None else None, p(mask, BF16, "mask") if gt is not None else None,
+                    int(C), int(H * W), float(sa), float(sb), int(renoise), int(self.mask_background), int(n))
         ops.launch_count += 1
         return (out, pred, prev) if want_prev_fp32 else (out, pred)
