@@ -81,7 +81,7 @@ def main():
         ev = [[[(vals[(w * 48 + t) * 8 + e] - t0) if vals[(w * 48 + t) * 8 + e] else None for e in range(8)] for t in range(48)]
               for w in range(18)]
         json.dump({"events": "softmax warp: 0 wait S, 1 S ready, 2 S loaded, 3 max / rescale done, 4 exps issued, 5 arrived on P; "
-                             "warp 16 (MMA issuer): 2s wait P_s, 2s+1 P_s ready", "clk": ev}, open(args.trace, "w"))
+                             "warp 16 (MMA issuer), per key tile: 4t+0 P(t, half 0) seen, 4t+1 its P V issued, 4t+2 P(t, half 1) seen, 4t+3 its P V and the next Q K^T issued", "clk": ev}, open(args.trace, "w"))
 
 
 if __name__ == "__main__":

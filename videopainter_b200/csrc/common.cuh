@@ -58,6 +58,18 @@ __device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) { return mbar_try_wait_a(smem_u32(bar), parity); }
+// Non-blocking probe (try_wait may suspend the thread for a system-dependent time when the phase is not complete).
+__device__ __forceinline__ bool mbar_test_wait_a(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ uint64_t global_timer_ns() {
   uint64_t t;
   asm volatile("mov.u64 %0, %globaltimer;\n" : "=l"(t));
@@ -81,6 +93,23 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
   mbar_wait_slow(bar, parity);
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { mbar_wait_a(smem_u32(bar), parity); }
+// Wait of a service warp (TMA producer, MMA issuer) whose work is not latency-critical: between two probes the warp sleeps,
+// so its spinning does not take issue slots from the compute warps of its SM sub-partition (measured in the attention kernel:
+// a spinning issuer warp slowed the four softmax warps it shares a sub-partition with by 20 %).
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t sleep_ns = 64) {
+  const uint32_t a = smem_u32(bar);
+  if (mbar_try_wait_a(a, parity)) return;
+  uint64_t t0 = 0;
+  uint32_t spins = 0;
+  do {
+    __nanosleep(sleep_ns);
+    if ((++spins & 0x3ff) == 0) {
+      const uint64_t now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) __trap();   // 4 s: a pipeline-protocol bug fails loudly instead of hanging the GPU
+    }
+  } while (!mbar_try_wait_a(a, parity));
+}
 
 // ------------------------------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor), loads only; results are written with plain vector stores
@@ -195,6 +224,26 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t* v) {
       : VP_R4(v, 0), VP_R4(v, 4), VP_R4(v, 8), VP_R4(v, 12)
       : "r"(taddr)
       : "memory");
+}
+// tcgen05.ld is asynchronous: its destination registers are only defined after tcgen05.wait::ld, but to the compiler they
+// are defined by the ld statement itself, so nothing stops it from scheduling their first use above a plain wait.  These
+// variants route the 32 registers through the wait (in/out operands): every later use depends on it.
+#define VP_RW4(v, i) "+r"(v[i]), "+r"(v[i + 1]), "+r"(v[i + 2]), "+r"(v[i + 3])
+__device__ __forceinline__ void tmem_wait_ld_dep32(uint32_t* v) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n"
+               : VP_RW4(v, 0), VP_RW4(v, 4), VP_RW4(v, 8), VP_RW4(v, 12), VP_RW4(v, 16), VP_RW4(v, 20), VP_RW4(v, 24), VP_RW4(v, 28)
+               :
+               : "memory");
+}
+__device__ __forceinline__ void reg_dep32(uint32_t* v) {      // same dependency, no instruction (after a wait that covers v too)
+  asm volatile(""
+               : VP_RW4(v, 0), VP_RW4(v, 4), VP_RW4(v, 8), VP_RW4(v, 12), VP_RW4(v, 16), VP_RW4(v, 20), VP_RW4(v, 24), VP_RW4(v, 28)
+               :
+               : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld_dep64(uint32_t* v) {
+  tmem_wait_ld_dep32(v);
+  reg_dep32(v + 32);
 }
 __device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t* v) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
