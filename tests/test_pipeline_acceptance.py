@@ -1,0 +1,88 @@
+"""Pipeline-level drop-in acceptance (harness in tests/pipeline_acceptance.py): the reference's own
+`CogVideoXI2VDualInpaintAnyLPipeline.__call__` over two chained windows x 4 steps.
+
+CPU half (here, when the reference is importable): the committed golden `tests/golden/pipeline_tiny.pt` is what the
+reference produces, and the installed forwards refuse to run without CUDA.
+GPU half (`-m gpu`): the same pipeline on cuda / bf16 with the reference's eager forwards and with
+`videopainter_b200.install()`; every noise_pred the pipeline receives is compared call by call."""
+import os
+
+import pytest
+import torch
+
+import pipeline_acceptance as PA
+
+needs_ref = pytest.mark.skipif(PA.reference_path() is None, reason="reference pipeline not available (no /root/reference, no baseline/_ref)")
+COS_MIN, REL_MAX = 0.9995, 3e-2
+
+
+def _cos(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float(a @ b / (a.norm() * b.norm() + 1e-30))
+
+
+def _rel(a, b):
+    return float((a.float() - b.float()).abs().max() / (b.float().abs().max() + 1e-30))
+
+
+@needs_ref
+@pytest.mark.parametrize("resample", [False, True])
+def test_golden_is_what_the_reference_pipeline_produces(resample):
+    ref = PA.load_reference()
+    gold = torch.load(PA.GOLDEN)["resample" if resample else "plain"]
+    preds, lat = PA.run(PA.build_pipeline(ref, "cpu", torch.float32, resample), resample)
+    assert len(preds) == len(gold["noise_preds"]) == 8          # 2 windows x 4 steps
+    for a, b in zip(preds, gold["noise_preds"]):
+        torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(lat, gold["latents"], rtol=1e-4, atol=1e-5)
+
+
+@needs_ref
+def test_installed_pipeline_refuses_cpu():
+    import videopainter_b200 as vp
+    ref = PA.load_reference()
+    pipe = PA.build_pipeline(ref, "cpu", torch.float32)
+    vp.install()
+    try:
+        with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
+            PA.run(pipe)
+    finally:
+        vp.uninstall()
+
+
+@needs_ref
+@pytest.mark.gpu
+@pytest.mark.parametrize("resample", [False, True])
+def test_installed_pipeline_matches_reference_on_gpu(resample):
+    """install() behind the real pipeline: 8 transformer calls (window 2 carries prev_hidden_states / prev_clip_weight /
+    prev_resample_mask through the pipeline's own plumbing, PIPE:962-988).  Both runs use bf16 on the same GPU, so the VAE,
+    scheduler and noise are identical and the only difference is the two forwards.  Per call: cosine >= 0.9995 and max-abs
+    error <= 3 % against the reference's eager bf16 result.  (The fp32 CPU golden is NOT comparable with either bf16 run: the
+    pipeline draws its noise in the model dtype, and a bf16 draw from the same seed is a different sample — first measured
+    run: both bf16 paths sit at cosine 0.62-0.71 against it, within 1e-4 of each other.  It is printed for the record only.)"""
+    import videopainter_b200 as vp
+    ref = PA.load_reference()
+    gold = torch.load(PA.GOLDEN)["resample" if resample else "plain"]
+    bf16 = torch.bfloat16
+    vp.uninstall()
+    eager, eager_lat = PA.run(PA.build_pipeline(ref, "cuda", bf16, resample), resample)
+    vp.install()
+    try:
+        pipe = PA.build_pipeline(ref, "cuda", bf16, resample)
+        from videopainter_b200 import ops
+        n0 = ops.launch_count
+        ours, ours_lat = PA.run(pipe, resample)
+        assert ops.launch_count > n0, "the patched forwards did not launch any B200 kernel"
+    finally:
+        vp.uninstall()
+    assert len(ours) == len(eager) == 8
+    for i, (a, e, g) in enumerate(zip(ours, eager, gold["noise_preds"])):
+        msg = (f"call {i}: ours vs eager-bf16 cos={_cos(a, e):.6f} rel={_rel(a, e):.4f} | vs fp32 golden: ours cos={_cos(a, g):.6f} "
+               f"rel={_rel(a, g):.4f}, eager cos={_cos(e, g):.6f} rel={_rel(e, g):.4f}")
+        print(msg)
+        assert not torch.isnan(a).any(), msg
+        assert _cos(a, e) >= COS_MIN and _rel(a, e) <= REL_MAX, msg
+        assert abs(_cos(a, g) - _cos(e, g)) <= 2e-3, msg          # equally far from the (different-noise) fp32 run
+    print(f"final latents: ours vs eager cos={_cos(ours_lat, eager_lat):.6f}; ours vs fp32 golden cos={_cos(ours_lat, gold['latents']):.6f}, "
+          f"eager vs fp32 golden cos={_cos(eager_lat, gold['latents']):.6f}")
+    assert _cos(ours_lat, eager_lat) >= 0.999
