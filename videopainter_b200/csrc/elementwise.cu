@@ -294,41 +294,60 @@ __global__ void __launch_bounds__(256) ln_double_kernel(const LnModParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// out[b, n] = sum_k act(in[b, k]) * W[n, k] + bias[n]   (fp32 in/out, bf16 weights), one warp per output column.
+// out[b, n] = sum_k act(in[b, k]) * W[n, k] + bias[n]   (fp32 in/out, bf16 weights).  Weight-bandwidth bound: the adaLN
+// tables of one forward stream 1.66 GB of weights through it (44 blocks x 2 x [18432, 512] bf16).
+// The activations (batch <= 8 rows of K floats) are transformed ONCE per CTA into shared memory — the first version
+// evaluated SiLU per (output row, batch, k), i.e. 1024 expf per 1 KiB of weights, and was MUFU-bound at 28 % of the HBM rate.
+// Each warp owns GEMV_RPW output rows, so that four independent 16-byte weight loads per lane are in flight.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int GEMV_MAX_B = 8;
-__global__ void __launch_bounds__(256) gemv_kernel(const float* __restrict__ in, const __nv_bfloat16* __restrict__ W,
-                                                   const __nv_bfloat16* __restrict__ bias, float* __restrict__ out, int B,
-                                                   int N, int K, int act_silu) {
+constexpr int GEMV_RPW = 4;
+constexpr int GEMV_WARPS = 8;
+__global__ void __launch_bounds__(GEMV_WARPS * 32) gemv_kernel(const float* __restrict__ in, const __nv_bfloat16* __restrict__ W,
+                                                               const __nv_bfloat16* __restrict__ bias, float* __restrict__ out,
+                                                               int B, int N, int K, int act_silu) {
+  extern __shared__ float gemv_x[];                                  // [B][K] activations after the optional SiLU
+  for (int i = threadIdx.x; i < B * K; i += GEMV_WARPS * 32) {
+    const float v = in[i];
+    gemv_x[i] = act_silu ? silu(v) : v;
+  }
+  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n = blockIdx.x * 8 + warp;
-  if (n >= N) return;
-  float acc[GEMV_MAX_B];
+  const int n0 = (blockIdx.x * GEMV_WARPS + warp) * GEMV_RPW;
+  if (n0 >= N) return;
+  float acc[GEMV_RPW][GEMV_MAX_B];
 #pragma unroll
-  for (int b = 0; b < GEMV_MAX_B; ++b) acc[b] = 0.f;
-  const __nv_bfloat16* w = W + (long long)n * K;
+  for (int r = 0; r < GEMV_RPW; ++r)
+#pragma unroll
+    for (int b = 0; b < GEMV_MAX_B; ++b) acc[r][b] = 0.f;
   for (int k0 = lane * 8; k0 < K; k0 += 256) {
-    float wf[8];
-    unpack8(ldg_nc_v4(w + k0), wf);
+    float wf[GEMV_RPW][8];
+#pragma unroll
+    for (int r = 0; r < GEMV_RPW; ++r) {
+      const int n = n0 + r < N ? n0 + r : N - 1;                       // rows past the end re-read the last row (not stored)
+      unpack8(ldg_nc_v4(W + (long long)n * K + k0), wf[r]);
+    }
 #pragma unroll
     for (int b = 0; b < GEMV_MAX_B; ++b) {
       if (b < B) {
-        const float4 a0 = __ldg(reinterpret_cast<const float4*>(in + (long long)b * K + k0));
-        const float4 a1 = __ldg(reinterpret_cast<const float4*>(in + (long long)b * K + k0) + 1);
-        float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float4 a0 = *reinterpret_cast<const float4*>(gemv_x + b * K + k0);
+        const float4 a1 = *reinterpret_cast<const float4*>(gemv_x + b * K + k0 + 4);
+        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float xv = act_silu ? silu(a[e]) : a[e];
-          acc[b] = fmaf(xv, wf[e], acc[b]);
-        }
+        for (int r = 0; r < GEMV_RPW; ++r)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[r][b] = fmaf(a[e], wf[r][e], acc[r][b]);
       }
     }
   }
 #pragma unroll
-  for (int b = 0; b < GEMV_MAX_B; ++b) {
-    if (b < B) {
-      const float r = warp_sum(acc[b]);
-      if (lane == 0) out[(long long)b * N + n] = r + (bias ? __bfloat162float(bias[n]) : 0.f);
+  for (int r = 0; r < GEMV_RPW; ++r) {
+#pragma unroll
+    for (int b = 0; b < GEMV_MAX_B; ++b) {
+      if (b < B) {
+        const float v = warp_sum(acc[r][b]);
+        if (lane == 0 && n0 + r < N) out[(long long)b * N + n0 + r] = v + (bias ? __bfloat162float(bias[n0 + r]) : 0.f);
+      }
     }
   }
 }
@@ -615,7 +634,15 @@ int launch_gemv(const float* in, const void* W, const void* bias, float* out, in
                 cudaStream_t st) {
   VP_REQUIRE(B > 0 && B <= GEMV_MAX_B, VP_ERR_UNSUPPORTED, "gemv: batch must be in [1, 8]");
   VP_REQUIRE(N > 0 && K > 0 && K % 8 == 0, VP_ERR_BAD_SHAPE, "gemv: K must be a multiple of 8");
-  gemv_kernel<<<(N + 7) / 8, 256, 0, st>>>(in, (const __nv_bfloat16*)W, (const __nv_bfloat16*)bias, out, B, N, K, act_silu);
+  const size_t smem = (size_t)B * K * sizeof(float);
+  VP_REQUIRE(smem <= 200 * 1024, VP_ERR_UNSUPPORTED, "gemv: batch x K activations do not fit in shared memory");
+  if (smem > 48 * 1024) {
+    const int rc = configure_once(reinterpret_cast<const void*>(gemv_kernel), 200 * 1024);
+    if (rc) return rc;
+  }
+  const int rows_per_cta = GEMV_WARPS * GEMV_RPW;
+  gemv_kernel<<<(N + rows_per_cta - 1) / rows_per_cta, GEMV_WARPS * 32, smem, st>>>(in, (const __nv_bfloat16*)W,
+                                                                                 (const __nv_bfloat16*)bias, out, B, N, K, act_silu);
   VP_CHECK_CUDA(cudaGetLastError());
   return VP_OK;
 }

@@ -58,8 +58,8 @@ inline PFN_tensorMapEncodeTiled encode_fn() {
 
 // bf16 tensor, innermost dimension contiguous, 128-byte swizzle, zero fill out of bounds.
 // dims/box are innermost-first; strides_bytes has rank-1 entries (dims 1..rank-1).
-inline int make_tmap_bf16(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims,
-                          const uint64_t* strides_bytes, const uint32_t* box) {
+inline int encode_tmap_bf16(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims,
+                            const uint64_t* strides_bytes, const uint32_t* box) {
   PFN_tensorMapEncodeTiled fn = encode_fn();
   if (!fn) return fail(VP_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return fail(VP_ERR_BAD_ALIGN, "TMA base pointer not 16-byte aligned");
@@ -80,6 +80,49 @@ inline int make_tmap_bf16(CUtensorMap* map, const void* ptr, int rank, const uin
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(VP_ERR_DRIVER, "cuTensorMapEncodeTiled failed", (int)r);
+  return VP_OK;
+}
+
+// A denoise step launches ~330 kernels with 2-5 tensor maps each, and every step of a run uses the same buffers (the
+// workspace and the weights are allocated once): the 128-byte descriptors are encoded once per (pointer, shape, box) and
+// looked up afterwards.  A CUtensorMap holds nothing but the address and the geometry, so a cached copy stays valid for
+// as long as a buffer of that geometry lives at that address; the table is simply dropped when it grows past a bound.
+struct TmapKey {
+  uint64_t w[12];
+  bool operator==(const TmapKey& o) const { return memcmp(w, o.w, sizeof(w)) == 0; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = 1469598103934665603ull;
+    for (uint64_t x : k.w) h = (h ^ x) * 1099511628211ull;
+    return (size_t)h;
+  }
+};
+inline int make_tmap_bf16(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                          const uint32_t* box) {
+  static std::mutex mu;
+  static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  TmapKey k{};
+  k.w[0] = reinterpret_cast<uint64_t>(ptr);
+  k.w[1] = (uint64_t)rank;
+  for (int i = 0; i < rank && i < 4; ++i) {
+    k.w[2 + i] = dims[i];
+    k.w[6 + i] = i > 0 ? strides_bytes[i - 1] : 0;
+    k.w[10] |= (uint64_t)box[i] << (16 * i);
+  }
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(k);
+    if (it != cache.end()) {
+      *map = it->second;
+      return VP_OK;
+    }
+  }
+  const int rc = encode_tmap_bf16(map, ptr, rank, dims, strides_bytes, box);
+  if (rc != VP_OK) return rc;
+  std::lock_guard<std::mutex> g(mu);
+  if (cache.size() > 8192) cache.clear();
+  cache.emplace(k, *map);
   return VP_OK;
 }
 
