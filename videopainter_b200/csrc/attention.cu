@@ -84,9 +84,9 @@ constexpr float RESCALE_THRESHOLD = VP_ATTN_RESCALE_LOG2;   // log2 units
 #else
 #define VP_SVC_WAIT(bar, parity) mbar_wait(bar, parity)
 #endif
-#ifndef VP_ATTN_PREFETCH_MAX
-#define VP_ATTN_PREFETCH_MAX 0               // 1: the next tile's row maximum is taken under this tile's exponentials (measured
-                                             // 12.2 ms instead of 8.8: the extra TMEM reads and their waits cost more than the scan)
+#ifndef VP_ATTN_GROUPS
+#define VP_ATTN_GROUPS 1                     // exponential groups per 64-key tile separated by scheduling fences (1, 2, 4, 8);
+                                             // measured 8.38 / 9.07 / 9.45 / 9.54 ms for 1 / 2 / 4 / 8: the fences cost more than they hide
 #endif
 #ifndef VP_ATTN_BALANCED
 #define VP_ATTN_BALANCED 1                   // 1: each service warp issues the MMAs of two streams; 0: one warp issues every Q K^T,
@@ -125,6 +125,14 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;\n" : "=f"(d) : "f"(a), "f"(b), "f"(c));
   return d;
+}
+// True, but neither the compiler nor ptxas can know (`bits` comes from a kernel parameter and is laundered through a
+// volatile asm, so two uses are not recognised as the same condition): a branch on it splits a basic block, i.e. it is an
+// instruction-scheduling fence.
+__device__ __forceinline__ bool opaque_true(uint32_t bits) {
+  uint32_t t;
+  asm volatile("mov.u32 %0, %1;\n" : "=r"(t) : "r"(bits));
+  return t != 0;
 }
 __device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -237,10 +245,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const float c = p.scale_log2;
     const uint64_t c2v = pack2(c, c);
     const uint64_t one2 = pack2(p.one, p.one);                // 1.0 the compiler cannot see: keeps x * 1 + y an FFMA2
+    const uint32_t one_bits = __float_as_uint(p.one);
     float m_used = -INFINITY;     // maximum the exponents are currently referenced to (raw score units)
     float row_sum = 0.f;
-    float m_next = -INFINITY;     // row maximum of the next tile, when it could be taken ahead of time (have_next)
-    bool have_next = false;
     // tiles whose tail keys do not exist (last tile of each segment), and how many of their 64 columns are real
     const int rag0 = n_t0 - 1, rag1 = n_t1 > 0 ? n_tiles - 1 : -1;
     const int val0 = p.kv_len0 - (n_t0 - 1) * BKV;
@@ -269,20 +276,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         }
       }
 
-      float tile_max;
-      if (have_next) {                                        // taken under the previous tile's exponentials (below)
-        tile_max = m_next;
-      } else {
-        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < 64; i += 8) {
-          mx0 = max3(mx0, __uint_as_float(sr[i + 0]), __uint_as_float(sr[i + 1]));
-          mx1 = max3(mx1, __uint_as_float(sr[i + 2]), __uint_as_float(sr[i + 3]));
-          mx2 = max3(mx2, __uint_as_float(sr[i + 4]), __uint_as_float(sr[i + 5]));
-          mx3 = max3(mx3, __uint_as_float(sr[i + 6]), __uint_as_float(sr[i + 7]));
-        }
-        tile_max = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      for (int i = 0; i < 64; i += 8) {
+        mx0 = max3(mx0, __uint_as_float(sr[i + 0]), __uint_as_float(sr[i + 1]));
+        mx1 = max3(mx1, __uint_as_float(sr[i + 2]), __uint_as_float(sr[i + 3]));
+        mx2 = max3(mx2, __uint_as_float(sr[i + 4]), __uint_as_float(sr[i + 5]));
+        mx3 = max3(mx3, __uint_as_float(sr[i + 6]), __uint_as_float(sr[i + 7]));
       }
+      const float tile_max = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
 
       // The P buffer of this tile's parity is free once P V of tile j - 2 has completed (issued two tiles ago: no stall).
       // One barrier per parity and every phase waited for, in order: parity waits can only tell two consecutive phases apart.
@@ -316,62 +318,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       const float neg_mc = -m_used * c;
       const uint64_t nmc2 = pack2(neg_mc, neg_mc);
       uint64_t acc0 = pack2(0.f, 0.f), acc1 = pack2(0.f, 0.f);
-      // 16 keys (one 32-byte k-step of the P V MMA) at a time: scale, exponentiate, accumulate the row sum, pack to bf16 and
-      // store the two 16-byte chunks to the P tile.
-      // Under these exponentials the row maximum of the NEXT tile is taken: its Q K^T was issued when this tile's scores left
-      // TMEM (s_free) and has normally completed by now, so its scores are read 32 columns at a time into registers that this
-      // tile no longer needs, max-scanned and dropped (they are read again at the top of the next iteration).  A warp issues
-      // in order and every exponential pair costs it the MUFU latency, so the MUFU pipe only fills up if most of a sub-partition's
-      // four warps are in this loop at any time: the stand-alone maximum scan was ~440 of the ~2500 clk of a tile.
-      bool pf = false;
-      float pm0 = -INFINITY, pm1 = -INFINITY;
-      uint32_t tmp[32];
-      const int vn = (j + 1 == rag0) ? val0 : ((j + 1 == rag1) ? val1 : BKV);   // real keys in the next tile
-      auto scan = [&](int n, int col0) {                      // max over tmp[0, n) = next-tile columns [col0, col0 + n)
+      // The 64 scores become 64 probabilities IN PLACE (sr), in groups of G = 64 / NG keys; `produce(g)` scales and exponentiates
+      // group g, `consume(g)` adds it to the row sum, packs it to bf16 and stores its 16-byte chunks to the P tile.
+      // Left alone (NG = 1) ptxas puts the consumer of an exponential pair one pair behind its MUFU.EX2 (`MUFU, MUFU,
+      // FFMA2(prev), F2FP(prev), MUFU, MUFU, F2FP(this pair) ...`) and re-derives that schedule from any source order inside a
+      // basic block.  NG > 1 separates the groups by branches it cannot remove (opaque_true), so that block k holds produce(k)
+      // and consume(k - 1), whose operands were issued a whole group earlier — an experiment on whether the short
+      // producer-consumer distance is what keeps the MUFU pipe at ~80 %.  It is not: every NG > 1 measured slower.
+      auto produce = [&](int g, int G) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          if (i < n) {
-            pm0 = max3(pm0, col0 + i + 0 < vn ? __uint_as_float(tmp[i + 0]) : -INFINITY,
-                       col0 + i + 1 < vn ? __uint_as_float(tmp[i + 1]) : -INFINITY);
-            pm1 = max3(pm1, col0 + i + 2 < vn ? __uint_as_float(tmp[i + 2]) : -INFINITY,
-                       col0 + i + 3 < vn ? __uint_as_float(tmp[i + 3]) : -INFINITY);
-          }
-        }
-      };
-#pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        // pieces sized to the score registers this tile has already consumed: 16 columns after chunk 0, 16 after chunk 1, 32
-        // after chunk 2; each piece is scanned one chunk later, when its load has long completed
-        if (VP_ATTN_PREFETCH_MAX && ch == 1) {
-          pf = (j + 1 < n_tiles) && __all_sync(0xffffffffu, mbar_test_wait_a(a_s_full, (j + 1) & 1));
-          if (pf) {
-            tc_fence_after();
-            tmem_ld_x16(tS, tmp);
-          }
-        }
-        if (VP_ATTN_PREFETCH_MAX && ch == 2 && pf) {
-          tmem_wait_ld_dep32(tmp);
-          scan(16, 0);
-          tmem_ld_x16(tS + 16, tmp);
-        }
-        if (VP_ATTN_PREFETCH_MAX && ch == 3 && pf) {
-          tmem_wait_ld_dep32(tmp);
-          scan(16, 16);
-          tmem_ld_x32(tS + 32, tmp);
-        }
-        uint32_t pk[8];
-        uint64_t y2[8];
-#pragma unroll
-        for (int pr = 0; pr < 8; ++pr)
-          y2[pr] = fma2(pack2(__uint_as_float(sr[(ch * 8 + pr) * 2]), __uint_as_float(sr[(ch * 8 + pr) * 2 + 1])), c2v, nmc2);
-#pragma unroll
-        for (int pr = 0; pr < 8; ++pr) {
+        for (int i = g * G; i < (g + 1) * G; i += 2) {
+          const uint64_t y2 = fma2(pack2(__uint_as_float(sr[i]), __uint_as_float(sr[i + 1])), c2v, nmc2);
           float e0, e1;
-          if ((pr & 7) < VP_ATTN_POLY_PER8) {
-            exp2_poly2(y2[pr], one2, e0, e1);
+          if (((i >> 1) & 7) < VP_ATTN_POLY_PER8) {
+            exp2_poly2(y2, one2, e0, e1);
           } else {
             float y0, y1;
-            unpack2(y2[pr], y0, y1);
+            unpack2(y2, y0, y1);
 #if defined(VP_ATTN_DEBUG_NOEXP)
             e0 = y0; e1 = y1;                                      // timing experiment only (wrong results)
 #else
@@ -379,19 +342,40 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             e1 = fast_exp2(y1);
 #endif
           }
-          pk[pr] = pack_bf16(e0, e1);
-          if (pr & 1) acc1 = fma2(pack2(e0, e1), one2, acc1);
-          else acc0 = fma2(pack2(e0, e1), one2, acc0);
+          sr[i] = __float_as_uint(e0);
+          sr[i + 1] = __float_as_uint(e1);
         }
-        const uint32_t p_dst = p_row + (j & 1) * P_BYTES;
-        sts_v4(p_dst + ((static_cast<uint32_t>(2 * ch) << 4) ^ p_xor), pk[0], pk[1], pk[2], pk[3]);
-        sts_v4(p_dst + ((static_cast<uint32_t>(2 * ch + 1) << 4) ^ p_xor), pk[4], pk[5], pk[6], pk[7]);
-      }
-      have_next = pf;
-      if (pf) {
-        tmem_wait_ld_dep32(tmp);
-        scan(32, 32);
-        m_next = fmaxf(pm0, pm1);
+      };
+      const uint32_t p_dst = p_row + (j & 1) * P_BYTES;
+      auto consume = [&](int g, int G) {
+#pragma unroll
+        for (int i = g * G; i < (g + 1) * G; i += 8) {             // 8 keys = one 16-byte chunk of the P row
+          uint32_t pk[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float e0 = __uint_as_float(sr[i + 2 * q]), e1 = __uint_as_float(sr[i + 2 * q + 1]);
+            pk[q] = pack_bf16(e0, e1);
+            if (q & 1) acc1 = fma2(pack2(e0, e1), one2, acc1);
+            else acc0 = fma2(pack2(e0, e1), one2, acc0);
+          }
+          sts_v4(p_dst + ((static_cast<uint32_t>(i >> 3) << 4) ^ p_xor), pk[0], pk[1], pk[2], pk[3]);
+        }
+      };
+      constexpr int NG = VP_ATTN_GROUPS;                           // 1 = one block (the compiler's own interleaving)
+      constexpr int G = 64 / NG;
+      if (NG == 1) {
+        produce(0, 64);
+        consume(0, 64);
+      } else {
+        produce(0, G);
+#pragma unroll
+        for (int g = 1; g < NG; ++g) {
+          if (opaque_true(one_bits)) {
+            produce(g, G);
+            consume(g - 1, G);
+          }
+        }
+        if (opaque_true(one_bits)) consume(NG - 1, G);
       }
       {
         float a0, a1;
