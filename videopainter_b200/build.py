@@ -8,7 +8,7 @@ import subprocess
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB = os.path.join(CSRC, "libvp_b200.so")
 TORCH_LIB = os.path.join(CSRC, "libvp_b200_torch.so")      # TORCH_LIBRARY(vp_b200) wrappers around the C ABI (torch_ops.cpp)
-SOURCES = ["capi.cu", "gemm.cu", "attention.cu", "attention_v1.cu", "attention_v2.cu", "elementwise.cu"]
+SOURCES = ["capi.cu", "gemm.cu", "attention.cu", "attention_v1.cu", "attention_v4.cu", "elementwise.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--threads", "4",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -1,24 +1,28 @@
-// SECOND DESIGN of the attention kernel (round 2, first half), kept selectable with VP_B200_ATTN=v2 for A/B measurements on one
-// box; the product kernel is attention.cu.  Finding: 64-key Q K^T tiles cost a quarter more tensor-pipe time (SS-MMAs re-read
-// the 4 KiB Q operand from shared memory for every 64 keys), which made this design tensor-bound at the MUFU bound's level.
+// FOURTH DESIGN of the attention kernel (round 2), kept selectable with VP_B200_ATTN=v4 for A/B measurements on one box; the
+// product kernel is attention.cu (the second design).  On one box, S = 17 776: this design 8.87 - 8.99 ms stand-alone and
+// 726 ms per denoise step, the product kernel 8.63 - 8.66 ms and 718 ms (profiles/r2_attention_design_notes.md).
 // Flash attention for the joint text+video sequence of CogVideoX (AP:2192-2197: non-causal, no mask, d_head = 64,
-// scale 1/8), tcgen05 + TMEM + TMA.  Second design of this kernel (round 2); the first one is kept in attention_v1.cu.
+// scale 1/8), tcgen05 + TMEM + TMA.
 //
-// d_head = 64 attention on B200 is bound by the exponentials, not by the tensor pipe: a 128 x 128 score tile needs 614 clk
-// of tcgen05.mma but 1024 clk of MUFU.EX2 per SM (profiles/r1_pipe_throughput_b200.txt).  The design goal is therefore that
-// the MUFU pipe of every SM sub-partition never waits:
-//
+// d_head = 64 attention on B200 is bound by the exponentials, not by the tensor pipe: per SM a 128 x 128 score tile needs
+// 1024 clk of MUFU.EX2 against 600-750 clk of tcgen05.mma (profiles/r1_pipe_throughput_b200.txt, r1_tcgen05_mma_issue_b200.txt).
+// What the measurements of this round showed (profiles/r2_attention_design_notes.md):
+//   - one warp cannot keep its sub-partition's MUFU busy (in-order issue; 2 warps per sub-partition reach ~75 %), four can;
+//   - any hand-off that makes the softmax warps wait for an MMA round trip (P ready -> P V -> next Q K^T -> S ready) costs
+//     ~1000 clk per key tile and leaves the MUFU idle for that long.
+// Hence:
 //   * one CTA = FOUR independent query tiles ("streams") of 128 rows of one (batch, head); 16 softmax warps, warp w serves
-//     stream w / 4 and TMEM lane quadrant w % 4, so every sub-partition hosts one warp of each stream and the four streams
-//     are at different phases of their tile loop (one loads S while the others exponentiate);
-//   * thread == query row over a 64-key tile: the row maximum and the row sum need no cross-thread exchange, no shared
-//     memory and no named barrier (the first design split a row over two warps);
-//   * TMEM (512 columns) = 4 x (S 64 | O 64).  P (bf16) is written over the first 32 columns of its own S: every thread
-//     has its whole S row in registers before it stores P, and the next Q K^T of the stream is issued behind the P V that
-//     reads P (tcgen05.mma of one thread execute in order), so the softmax warps never wait for the P V MMA;
-//   * one MMA-issuing warp serves the streams round-robin (P V_s(j), then Q K_s(j+1)^T), which keeps them staggered;
-//   * K/V tiles (64 keys, 8 KiB each) stream through a TMA ring shared by the four streams: 512 query rows per K/V byte
-//     fetched from L2 (the first design: 256);
+//     stream w / 4 and TMEM lane quadrant w % 4 — every sub-partition hosts one warp of each stream;
+//   * thread == query row over a 64-key tile: row maximum and row sum need no cross-thread exchange;
+//   * the scores leave TMEM as soon as they are computed: each thread loads its S row into registers and releases the S
+//     columns at once (s_free), so the MMA warp issues the stream's NEXT Q K^T while the exponentials of this tile are still
+//     running — S(j+1) is complete long before the softmax asks for it;
+//   * P (bf16) goes to shared memory (128B-swizzled K-major tile, the layout TMA gives Q), not over S in TMEM, which is what
+//     decouples the next Q K^T from this tile's P V; O += P V is an SS-MMA (48 clk per 128x64x16 step instead of 45); the P
+//     tiles are double-buffered, so the softmax does not wait for the P V of the previous tile either;
+//   * four service warps, one per SM sub-partition, share the MMA issue evenly (two issue Q K^T, two issue P V, for two
+//     streams each; two of them also feed the K and V rings by TMA);
+//   * TMEM (512 columns) = 4 x (S 64 | O 64); K/V tiles (64 keys) stream through a TMA ring shared by the four streams;
 //   * lazy rescaling: the running maximum is only refreshed when it grows by more than 2^8, so O is rarely touched;
 //   * optionally a share of the exponentials is evaluated by a polynomial on the FMA pipe (VP_ATTN_POLY_PER8).
 //
@@ -27,7 +31,6 @@
 #include "attention.cuh"
 #include "host_util.cuh"
 
-#include <mutex>
 #include <stdlib.h>
 
 namespace vp {
@@ -40,17 +43,21 @@ constexpr int NS = 4;            // streams (query tiles) per CTA
 constexpr int BKV = 64;          // keys per tile
 constexpr int DH = 64;           // head dim
 #undef VP_ATTN_KV_STAGES
-#define VP_ATTN_KV_STAGES 6
+#define VP_ATTN_KV_STAGES 2                  // Q 64 KiB + P 128 KiB leave room for two 8 KiB K and V stages (each tile is needed
+                                             // by the first stream a whole round after the last stream released its stage)
 constexpr int ST = VP_ATTN_KV_STAGES;
 constexpr int Q_BYTES = BQ * DH * 2;        // 16 KiB
+constexpr int P_BYTES = BQ * BKV * 2;       // 16 KiB: one stream's P tile, same layout as a Q tile
 constexpr int KV_BYTES = BKV * DH * 2;      // 8 KiB
 constexpr int SMEM_Q = 0;
-constexpr int SMEM_K = NS * Q_BYTES;
+constexpr int SMEM_P = SMEM_Q + NS * Q_BYTES;
+constexpr int SMEM_K = SMEM_P + 2 * NS * P_BYTES;   // P tiles are double-buffered by key-tile parity
 constexpr int SMEM_V = SMEM_K + ST * KV_BYTES;
 constexpr int SMEM_BAR = SMEM_V + ST * KV_BYTES;
 constexpr int SMEM_BYTES = SMEM_BAR + 512 + 1024;
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
 constexpr int NUM_SOFTMAX_WARPS = 4 * NS;
-constexpr int NUM_THREADS = (NUM_SOFTMAX_WARPS + 4) * 32;   // 16 softmax + TMA + MMA + 2 idle (setmaxnreg: whole warpgroups)
+constexpr int NUM_THREADS = (NUM_SOFTMAX_WARPS + 4) * 32;   // 16 softmax + 4 service warps (TMA producers / MMA issuers)
 #undef VP_ATTN_SOFTMAX_REGS
 #undef VP_ATTN_OTHER_REGS
 #define VP_ATTN_SOFTMAX_REGS 104
@@ -58,24 +65,31 @@ constexpr int NUM_THREADS = (NUM_SOFTMAX_WARPS + 4) * 32;   // 16 softmax + TMA 
 constexpr int SOFTMAX_REGS = VP_ATTN_SOFTMAX_REGS, OTHER_REGS = VP_ATTN_OTHER_REGS;
 static_assert(512 * SOFTMAX_REGS + 128 * OTHER_REGS <= 640 * 96, "register pool of the CTA exceeded");
 constexpr uint32_t TMEM_COLS = 512;
-constexpr uint32_t COL_STREAM = 128, COL_S = 0, COL_O = 64;   // P aliases S columns [0, 32)
-#ifndef VP_ATTN_POLY_PER8
-#define VP_ATTN_POLY_PER8 0                  // of every 8 element pairs, this many take the polynomial exp2 (0..8)
-#endif
+constexpr uint32_t COL_STREAM = 128, COL_S = 0, COL_O = 64;
+#undef VP_ATTN_POLY_PER8
+#define VP_ATTN_POLY_PER8 1                  // of every 8 element pairs, this many take the polynomial exp2 (0..8)
 #ifndef VP_ATTN_RESCALE_LOG2
 #define VP_ATTN_RESCALE_LOG2 8.0f
 #endif
 constexpr float RESCALE_THRESHOLD = VP_ATTN_RESCALE_LOG2;   // log2 units
-#ifndef VP_ATTN_CHUNK_PAIRS
-#define VP_ATTN_CHUNK_PAIRS 8                // element pairs per P store (4, 8, 16: tcgen05.st x4 / x8 / x16)
+#ifndef VP_ATTN_SVC_SLEEP_NS
+#define VP_ATTN_SVC_SLEEP_NS 0               // >0: service warps sleep this long between barrier probes (nanosleep is ~1 us coarse:
+                                             // it delays the next Q K^T by a third of a tile and was measured no faster)
 #endif
-#ifndef VP_ATTN_MMA_WARPS
-#define VP_ATTN_MMA_WARPS 2                  // MMA-issuing warps (1 or 2): warp m serves streams m, m + NMMA, ...
+#if VP_ATTN_SVC_SLEEP_NS > 0
+#define VP_SVC_WAIT(bar, parity) mbar_wait_relaxed(bar, parity, VP_ATTN_SVC_SLEEP_NS)
+#else
+#define VP_SVC_WAIT(bar, parity) mbar_wait(bar, parity)
 #endif
-constexpr int NMMA = VP_ATTN_MMA_WARPS;
-static_assert(NMMA == 1 || NMMA == 2, "one or two MMA-issuing warps");
+#ifndef VP_ATTN_GROUPS
+#define VP_ATTN_GROUPS 1                     // exponential groups per 64-key tile separated by scheduling fences (1, 2, 4, 8);
+                                             // measured 8.38 / 9.07 / 9.45 / 9.54 ms for 1 / 2 / 4 / 8: the fences cost more than they hide
+#endif
+#ifndef VP_ATTN_BALANCED
+#define VP_ATTN_BALANCED 1                   // 1: each service warp issues the MMAs of two streams; 0: one warp issues every Q K^T,
+#endif                                       // another every P V, the TMA producers only produce
 #undef VP_ATTN_TRACE
-#define VP_ATTN_TRACE 0                      // the trace facility belongs to the current design (attention.cu)
+#define VP_ATTN_TRACE 0                      // the trace facility belongs to the product kernel (attention.cu)
 
 #if VP_ATTN_TRACE
 constexpr int TRACE_TILES = 48, TRACE_EV = 8, TRACE_WARPS = 18;
@@ -107,6 +121,17 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;\n" : "=f"(d) : "f"(a), "f"(b), "f"(c));
   return d;
+}
+// True, but neither the compiler nor ptxas can know (`bits` comes from a kernel parameter and is laundered through a
+// volatile asm, so two uses are not recognised as the same condition): a branch on it splits a basic block, i.e. it is an
+// instruction-scheduling fence.
+__device__ __forceinline__ bool opaque_true(uint32_t bits) {
+  uint32_t t;
+  asm volatile("mov.u32 %0, %1;\n" : "=r"(t) : "r"(bits));
+  return t != 0;
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
 // exp2 of two values on the FMA / ALU pipes (no MUFU): Cody-Waite split with the 1.5*2^23 rounding trick and a
@@ -141,7 +166,10 @@ struct Bars {
   uint64_t q_full;
   uint64_t k_full[ST], k_empty[ST];
   uint64_t v_full[ST], v_empty[ST];
-  uint64_t s_full[NS], p_full[NS], o_done[NS];
+  uint64_t s_full[NS];      // Q K^T of the stream's next tile has landed in its S columns              (tcgen05.commit)
+  uint64_t s_free[NS];      // every thread of the stream holds its S row in registers                  (128 arrivals)
+  uint64_t p_full[NS][2];   // the stream's P tile of an even / odd key tile is in shared memory        (128 arrivals)
+  uint64_t o_done[NS][2];   // the stream's P V of an even / odd tile has completed: O is up to date, that P buffer is free
   uint32_t tmem_slot;
 };
 static_assert(sizeof(Bars) <= 512, "barrier block too large");
@@ -175,14 +203,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     mbar_init(&bars->q_full, 1);
     for (int i = 0; i < ST; ++i) {
       mbar_init(&bars->k_full[i], 1);
-      mbar_init(&bars->k_empty[i], NMMA);               // every MMA-issuing warp commits once per stage
+      mbar_init(&bars->k_empty[i], VP_ATTN_BALANCED ? 2 : 1);   // one tcgen05.commit from each Q K^T issuer
       mbar_init(&bars->v_full[i], 1);
-      mbar_init(&bars->v_empty[i], NMMA);
+      mbar_init(&bars->v_empty[i], VP_ATTN_BALANCED ? 2 : 1);   // one from each P V issuer
     }
     for (int s = 0; s < NS; ++s) {
       mbar_init(&bars->s_full[s], 1);
-      mbar_init(&bars->p_full[s], BQ);
-      mbar_init(&bars->o_done[s], 1);
+      mbar_init(&bars->s_free[s], BQ);
+      mbar_init(&bars->p_full[s][0], BQ);
+      mbar_init(&bars->p_full[s][1], BQ);
+      mbar_init(&bars->o_done[s][0], 1);
+      mbar_init(&bars->o_done[s][1], 1);
     }
     fence_barrier_init();
   }
@@ -199,13 +230,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const int quad = warp & 3;                                // TMEM lane quadrant (hardware: warp id % 4)
     const int row = quad * 32 + lane;
     const uint32_t a_s_full = smem_u32(&bars->s_full[s]);
-    const uint32_t a_p_full = smem_u32(&bars->p_full[s]);
-    const uint32_t a_o_done = smem_u32(&bars->o_done[s]);
+    const uint32_t a_s_free = smem_u32(&bars->s_free[s]);
+    const uint32_t a_p_full = smem_u32(&bars->p_full[s][0]);   // [0] even tiles, [1] (+8 bytes) odd tiles
+    const uint32_t a_o_done = smem_u32(&bars->o_done[s][0]);   // [0] even tiles, [1] (+8 bytes) odd tiles
     const uint32_t tS = tmem_base + s * COL_STREAM + COL_S + (static_cast<uint32_t>(quad * 32) << 16);
     const uint32_t tO = tS + (COL_O - COL_S);
+    // this thread's row of the stream's P tile: 128 bytes, 16-byte chunk c stored at c ^ (row & 7) (SWIZZLE_128B, K-major)
+    const uint32_t p_row = smem_u32(smem + SMEM_P) + s * 2 * P_BYTES + row * 128;   // buffer of odd tiles: + P_BYTES
+    const uint32_t p_xor = static_cast<uint32_t>(row & 7) << 4;
     const float c = p.scale_log2;
     const uint64_t c2v = pack2(c, c);
     const uint64_t one2 = pack2(p.one, p.one);                // 1.0 the compiler cannot see: keeps x * 1 + y an FFMA2
+    const uint32_t one_bits = __float_as_uint(p.one);
     float m_used = -INFINITY;     // maximum the exponents are currently referenced to (raw score units)
     float row_sum = 0.f;
     // tiles whose tail keys do not exist (last tile of each segment), and how many of their 64 columns are real
@@ -222,7 +258,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       uint32_t sr[64];
       tmem_ld_x32(tS + 0, sr + 0);
       tmem_ld_x32(tS + 32, sr + 32);
-      tmem_wait_ld();
+      tmem_wait_ld_dep64(sr);
+      tc_fence_before();
+      mbar_arrive_a(a_s_free);                                // the stream's next Q K^T may overwrite S now
       VP_TRACE(warp, j, 2);
 
       if (j == rag0 || j == rag1) {                           // ragged last tile of a segment
@@ -244,6 +282,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
       const float tile_max = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
 
+      // The P buffer of this tile's parity is free once P V of tile j - 2 has completed (issued two tiles ago: no stall).
+      // One barrier per parity and every phase waited for, in order: parity waits can only tell two consecutive phases apart.
+      if (j > 1) mbar_wait_a(a_o_done + (j & 1) * 8, ((j >> 1) - 1) & 1);
       const bool need = (tile_max - m_used) * c > RESCALE_THRESHOLD;   // true at j == 0 (m_used = -inf)
       if (__any_sync(0xffffffffu, need)) {                             // tcgen05.ld / st are warp-collective
         float factor = 1.0f;
@@ -253,7 +294,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           row_sum *= factor;
         }
         if (j > 0) {
-          mbar_wait_a(a_o_done, (j - 1) & 1);                          // P_{j-1} V_{j-1} has landed in O
+          mbar_wait_a(a_o_done + ((j - 1) & 1) * 8, ((j - 1) >> 1) & 1);   // P V of the previous tile has landed in O
           tc_fence_after();
           // rare path: eight columns at a time, so that the 64 live score registers are not spilled around it
 #pragma unroll 1
@@ -261,34 +302,35 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             uint32_t o[8];
             tmem_ld_x8(tO + c8, o);
             tmem_wait_ld();
+            asm volatile("" : "+r"(o[0]), "+r"(o[1]), "+r"(o[2]), "+r"(o[3]), "+r"(o[4]), "+r"(o[5]), "+r"(o[6]), "+r"(o[7]));
 #pragma unroll
             for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
             tmem_st_x8(tO + c8, o);
           }
+          tmem_wait_st();
         }
       }
       VP_TRACE(warp, j, 3);
       const float neg_mc = -m_used * c;
       const uint64_t nmc2 = pack2(neg_mc, neg_mc);
       uint64_t acc0 = pack2(0.f, 0.f), acc1 = pack2(0.f, 0.f);
-      // CP pairs at a time: scale, exponentiate, accumulate the row sum, pack to bf16 and store the packed words over the
-      // (already consumed) S columns right away — few live registers, MUFU / FMA / ALU work of neighbouring chunks overlaps
-      constexpr int CP = VP_ATTN_CHUNK_PAIRS;
+      // The 64 scores become 64 probabilities IN PLACE (sr), in groups of G = 64 / NG keys; `produce(g)` scales and exponentiates
+      // group g, `consume(g)` adds it to the row sum, packs it to bf16 and stores its 16-byte chunks to the P tile.
+      // Left alone (NG = 1) ptxas puts the consumer of an exponential pair one pair behind its MUFU.EX2 (`MUFU, MUFU,
+      // FFMA2(prev), F2FP(prev), MUFU, MUFU, F2FP(this pair) ...`) and re-derives that schedule from any source order inside a
+      // basic block.  NG > 1 separates the groups by branches it cannot remove (opaque_true), so that block k holds produce(k)
+      // and consume(k - 1), whose operands were issued a whole group earlier — an experiment on whether the short
+      // producer-consumer distance is what keeps the MUFU pipe at ~80 %.  It is not: every NG > 1 measured slower.
+      auto produce = [&](int g, int G) {
 #pragma unroll
-      for (int ch = 0; ch < 32 / CP; ++ch) {
-        uint32_t pk[CP];
-        uint64_t y2[CP];
-#pragma unroll
-        for (int pr = 0; pr < CP; ++pr)
-          y2[pr] = fma2(pack2(__uint_as_float(sr[(ch * CP + pr) * 2]), __uint_as_float(sr[(ch * CP + pr) * 2 + 1])), c2v, nmc2);
-#pragma unroll
-        for (int pr = 0; pr < CP; ++pr) {
+        for (int i = g * G; i < (g + 1) * G; i += 2) {
+          const uint64_t y2 = fma2(pack2(__uint_as_float(sr[i]), __uint_as_float(sr[i + 1])), c2v, nmc2);
           float e0, e1;
-          if ((pr & 7) < VP_ATTN_POLY_PER8) {
-            exp2_poly2(y2[pr], one2, e0, e1);
+          if (((i >> 1) & 7) < VP_ATTN_POLY_PER8) {
+            exp2_poly2(y2, one2, e0, e1);
           } else {
             float y0, y1;
-            unpack2(y2[pr], y0, y1);
+            unpack2(y2, y0, y1);
 #if defined(VP_ATTN_DEBUG_NOEXP)
             e0 = y0; e1 = y1;                                      // timing experiment only (wrong results)
 #else
@@ -296,13 +338,40 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             e1 = fast_exp2(y1);
 #endif
           }
-          pk[pr] = pack_bf16(e0, e1);
-          if (pr & 1) acc1 = fma2(pack2(e0, e1), one2, acc1);
-          else acc0 = fma2(pack2(e0, e1), one2, acc0);
+          sr[i] = __float_as_uint(e0);
+          sr[i + 1] = __float_as_uint(e1);
         }
-        if (CP == 4) tmem_st_x4(tS + ch * CP, pk);
-        else if (CP == 8) tmem_st_x8(tS + ch * CP, pk);
-        else tmem_st_x16(tS + ch * CP, pk);
+      };
+      const uint32_t p_dst = p_row + (j & 1) * P_BYTES;
+      auto consume = [&](int g, int G) {
+#pragma unroll
+        for (int i = g * G; i < (g + 1) * G; i += 8) {             // 8 keys = one 16-byte chunk of the P row
+          uint32_t pk[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float e0 = __uint_as_float(sr[i + 2 * q]), e1 = __uint_as_float(sr[i + 2 * q + 1]);
+            pk[q] = pack_bf16(e0, e1);
+            if (q & 1) acc1 = fma2(pack2(e0, e1), one2, acc1);
+            else acc0 = fma2(pack2(e0, e1), one2, acc0);
+          }
+          sts_v4(p_dst + ((static_cast<uint32_t>(i >> 3) << 4) ^ p_xor), pk[0], pk[1], pk[2], pk[3]);
+        }
+      };
+      constexpr int NG = VP_ATTN_GROUPS;                           // 1 = one block (the compiler's own interleaving)
+      constexpr int G = 64 / NG;
+      if (NG == 1) {
+        produce(0, 64);
+        consume(0, 64);
+      } else {
+        produce(0, G);
+#pragma unroll
+        for (int g = 1; g < NG; ++g) {
+          if (opaque_true(one_bits)) {
+            produce(g, G);
+            consume(g - 1, G);
+          }
+        }
+        if (opaque_true(one_bits)) consume(NG - 1, G);
       }
       {
         float a0, a1;
@@ -310,14 +379,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         row_sum += a0 + a1;
       }
       VP_TRACE(warp, j, 4);
-      tmem_wait_st();
-      tc_fence_before();
-      mbar_arrive_a(a_p_full);
+      fence_proxy_async_smem();                               // generic-proxy stores -> visible to tcgen05.mma (async proxy)
+      tc_fence_before();                                      // orders the rescale path's tcgen05.st before the P V MMA
+      // (one barrier per tile parity, like o_done: a stream may finish P(j + 1) before the issuer has looked at P(j) of a
+      //  slower stream, and a parity wait cannot tell phases j and j + 2 of one barrier apart)
+      mbar_arrive_a(a_p_full + (j & 1) * 8);
       VP_TRACE(warp, j, 5);
     }
 
     // -------- epilogue: O / l -> bf16 -> out[b, q, h*64 ...] --------
-    mbar_wait_a(a_o_done, (n_tiles - 1) & 1);
+    mbar_wait_a(a_o_done + ((n_tiles - 1) & 1) * 8, ((n_tiles - 1) >> 1) & 1);
     tc_fence_after();
     const int q_row = q0 + s * BQ + row;
     const bool row_ok = q_row < p.seq_q;
@@ -332,7 +403,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     for (int hlf = 0; hlf < 2; ++hlf) {
       uint32_t o[32];
       tmem_ld_x32(tO + hlf * 32, o);
-      tmem_wait_ld();
+      tmem_wait_ld_dep32(o);
       if (row_ok) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -356,100 +427,120 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(OTHER_REGS));
     // Producer and MMA loops run warp-wide; only the asynchronous instructions are issued by one elected lane, so that
     // descriptor arithmetic stays on the uniform datapath (a divergent single thread costs ~100 clk per tcgen05.mma).
-    if (warp == NUM_SOFTMAX_WARPS) {
-      // ================================================ TMA producer ============================================
-      if (elect_one()) {
-        mbar_arrive_expect_tx(&bars->q_full, NS * Q_BYTES);
-#pragma unroll
-        for (int s = 0; s < NS; ++s)
-          tma_load_3d(smem + SMEM_Q + s * Q_BYTES, &tmap_q, &bars->q_full, 0, q0 + s * BQ, bh, kEvictFirst);
-      }
-      __syncwarp();
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int j = 0; j < n_tiles; ++j) {
-        const bool seg1 = j >= n_t0;
-        const int kv0 = (seg1 ? j - n_t0 : j) * BKV;
-        mbar_wait(&bars->k_empty[stage], phase ^ 1);
-        if (elect_one()) {
-          mbar_arrive_expect_tx(&bars->k_full[stage], KV_BYTES);
-          tma_load_3d(smem + SMEM_K + stage * KV_BYTES, seg1 ? &tmap_k1 : &tmap_k0, &bars->k_full[stage], 0, kv0, bh,
-                      kEvictLast);
-        }
-        __syncwarp();
-        mbar_wait(&bars->v_empty[stage], phase ^ 1);
-        if (elect_one()) {
-          mbar_arrive_expect_tx(&bars->v_full[stage], KV_BYTES);
-          tma_load_3d(smem + SMEM_V + stage * KV_BYTES, seg1 ? &tmap_v1 : &tmap_v0, &bars->v_full[stage], 0, kv0, bh,
-                      kEvictLast);
-        }
-        __syncwarp();
-        if (++stage == ST) { stage = 0; phase ^= 1; }
-      }
-    } else if (warp <= NUM_SOFTMAX_WARPS + NMMA) {
-      // ================================================ MMA issuers =============================================
-      // Per stream s and key tile j:  S_s = Q_s K_j^T (SS-MMA 128x64x64)  ->  softmax writes P_s over S_s  ->
-      // O_s += P_s V_j (TS-MMA 128x64x64, P from TMEM, V as MN-major B)  ->  S_s = Q_s K_{j+1}^T behind it, in order.
-      // tcgen05.mma issue blocks while the pipe's short queue is full, so a single issuer leaves the pipe idle whenever it
-      // polls the next stream's P barrier (measured with VP_ATTN_TRACE: ~80 clk per stream and tile); with two issuers (streams
-      // {0, 2} and {1, 3}) one of them always has MMAs queued.  Ordering is only needed inside a stream, i.e. inside a warp.
-      const int mw = warp - (NUM_SOFTMAX_WARPS + 1);
-      const int s_last = mw + NS - NMMA;
+    // Four service warps, one per SM sub-partition.  Issuing a tcgen05.mma costs its sub-partition issue time (measured: the
+    // softmax warps sharing a sub-partition with a warp that issues 16 MMAs per round run 17 % slower than the others), so the
+    // 32 MMAs of a round are spread evenly: 8 per sub-partition.
+    //   warp 16: Q and K tiles by TMA, Q K^T of streams 0, 1        warp 17: Q K^T of streams 2, 3
+    //   warp 18: P V of streams 0, 1                                 warp 19: V tiles by TMA, P V of streams 2, 3
+    const int svc = warp - NUM_SOFTMAX_WARPS;
+    // streams whose Q K^T (svc 0, 1) / P V (svc 2, 3) this warp issues: NI of them from s_lo on
+#if VP_ATTN_BALANCED
+    constexpr int NI = 2;
+    const int s_lo = (svc & 1) * 2;
+    const bool issuer = true;
+#else
+    constexpr int NI = NS;                                           // warp 17 issues every Q K^T, warp 18 every P V
+    const int s_lo = 0;
+    const bool issuer = svc == 1 || svc == 2;
+#endif
+    if (svc <= 1) {
+      // ================================================ Q K^T issuers (+ K producer) ============================
+      // S_s(j) = Q_s K_j^T (SS-MMA 128x64x64) as soon as the stream's threads have taken S_s(j-1) into registers.
       constexpr uint32_t idesc_qk = make_idesc_bf16(BQ, BKV, 0, 0);
-      constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, DH, 0, 1);     // B = V, MN-major
       const uint32_t sq = smem_u32(smem + SMEM_Q);
       const uint32_t sk = smem_u32(smem + SMEM_K);
-      const uint32_t sv = smem_u32(smem + SMEM_V);
-
-      auto issue_qk = [&](int s, int stage) {
+      auto load_k = [&](int j) {                                       // K tile j into stage j % ST (warp 16 only)
+        const int stage = j % ST;
+        const bool seg1 = j >= n_t0;
+        const int kv0 = (seg1 ? j - n_t0 : j) * BKV;
+        VP_SVC_WAIT(&bars->k_empty[stage], ((j / ST) & 1) ^ 1);
         if (elect_one()) {
-          const uint64_t adesc = make_desc_sw128(sq + s * Q_BYTES, 1024, 0);
-          const uint64_t bdesc = make_desc_sw128(sk + stage * KV_BYTES, 1024, 0);
-#pragma unroll
-          for (int k = 0; k < DH / 16; ++k)
-            mma_ss(tmem_base + s * COL_STREAM + COL_S, adesc + 2 * k, bdesc + 2 * k, idesc_qk, k != 0);
-          tc_commit(&bars->s_full[s]);
-          if (s == s_last) tc_commit(&bars->k_empty[stage]);
+          mbar_arrive_expect_tx(&bars->k_full[stage], KV_BYTES);
+          tma_load_3d(smem + SMEM_K + stage * KV_BYTES, seg1 ? &tmap_k1 : &tmap_k0, &bars->k_full[stage], 0, kv0, bh, kEvictLast);
         }
         __syncwarp();
       };
-
-      mbar_wait(&bars->q_full, 0);
-      mbar_wait(&bars->k_full[0], 0);
-      tc_fence_after();
-      for (int s = mw; s < NS; s += NMMA) issue_qk(s, 0);
-
+      if (svc == 0) {
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&bars->q_full, NS * Q_BYTES);
+#pragma unroll
+          for (int s = 0; s < NS; ++s)
+            tma_load_3d(smem + SMEM_Q + s * Q_BYTES, &tmap_q, &bars->q_full, 0, q0 + s * BQ, bh, kEvictFirst);
+        }
+        __syncwarp();
+        for (int j = 0; j < ST - 1 && j < n_tiles; ++j) load_k(j);
+      }
+      VP_SVC_WAIT(&bars->q_full, 0);
       int stage = 0;
       uint32_t phase = 0;
       for (int j = 0; j < n_tiles; ++j) {
-        const uint32_t par = j & 1;
-        const int nstage = (stage + 1 == ST) ? 0 : stage + 1;
-        const uint32_t nphase = (stage + 1 == ST) ? (phase ^ 1) : phase;
-        const bool more = j + 1 < n_tiles;
-        for (int s = mw; s < NS; s += NMMA) {
-          VP_TRACE(16 + mw, j, (s / NMMA) * 2);
-          mbar_wait(&bars->p_full[s], par);                    // P_s(j) is in TMEM
-          if (s == mw) {
-            mbar_wait(&bars->v_full[stage], phase);
-            if (more) mbar_wait(&bars->k_full[nstage], nphase);
-          }
-          tc_fence_after();
-          VP_TRACE(16 + mw, j, (s / NMMA) * 2 + 1);
-          if (elect_one()) {
-            // V tile [64 keys][64 d] as MN-major B: 8-key groups are 1024 B apart, 16 keys per MMA = 2048 B
-            const uint64_t vdesc = make_desc_sw128(sv + stage * KV_BYTES, 1024, 1024);
-            const uint32_t tP = tmem_base + s * COL_STREAM + COL_S;
-            const uint32_t tOs = tmem_base + s * COL_STREAM + COL_O;
+        // K tile j + ST - 1 goes into the stage that tile j - 1 used: free once all four Q K^T of tile j - 1 have completed
+        if (svc == 0 && j + ST - 1 < n_tiles) load_k(j + ST - 1);
+        if (!issuer) continue;
+        VP_SVC_WAIT(&bars->k_full[stage], phase);
 #pragma unroll
-            for (int k = 0; k < BKV / 16; ++k) mma_ts(tOs, tP + k * 8, vdesc + (uint64_t)(128 * k), idesc_pv, (j | k) != 0);
-            tc_commit(&bars->o_done[s]);
-            if (s == s_last) tc_commit(&bars->v_empty[stage]);
+        for (int si = 0; si < NI; ++si) {
+          const int s = s_lo + si;
+          if (j > 0) VP_SVC_WAIT(&bars->s_free[s], (j - 1) & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t adesc = make_desc_sw128(sq + s * Q_BYTES, 1024, 0);
+            const uint64_t bdesc = make_desc_sw128(sk + stage * KV_BYTES, 1024, 0);
+#pragma unroll
+            for (int k = 0; k < DH / 16; ++k)
+              mma_ss(tmem_base + s * COL_STREAM + COL_S, adesc + 2 * k, bdesc + 2 * k, idesc_qk, k != 0);
+            tc_commit(&bars->s_full[s]);
+            if (si == NI - 1) tc_commit(&bars->k_empty[stage]);        // one arrival per tile from each Q K^T issuer
           }
           __syncwarp();
-          if (more) issue_qk(s, nstage);
+          VP_TRACE(16 + svc, j, s & 3);
         }
-        stage = nstage;
-        phase = nphase;
+        if (++stage == ST) { stage = 0; phase ^= 1; }
+      }
+    } else {
+      // ================================================ P V issuers (+ V producer) ==============================
+      // O_s += P_s(j) V_j (SS-MMA 128x64x64, P from shared memory, V as MN-major B) once the stream's P tile is complete.
+      constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, DH, 0, 1);     // B = V, MN-major
+      const uint32_t sp = smem_u32(smem + SMEM_P);
+      const uint32_t sv = smem_u32(smem + SMEM_V);
+      auto load_v = [&](int j) {                                       // V tile j into stage j % ST (warp 19 only)
+        const int stage = j % ST;
+        const bool seg1 = j >= n_t0;
+        const int kv0 = (seg1 ? j - n_t0 : j) * BKV;
+        VP_SVC_WAIT(&bars->v_empty[stage], ((j / ST) & 1) ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&bars->v_full[stage], KV_BYTES);
+          tma_load_3d(smem + SMEM_V + stage * KV_BYTES, seg1 ? &tmap_v1 : &tmap_v0, &bars->v_full[stage], 0, kv0, bh, kEvictLast);
+        }
+        __syncwarp();
+      };
+      if (svc == 3)
+        for (int j = 0; j < ST - 1 && j < n_tiles; ++j) load_v(j);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < n_tiles; ++j) {
+        if (svc == 3 && j + ST - 1 < n_tiles) load_v(j + ST - 1);
+        if (!issuer) continue;
+        VP_SVC_WAIT(&bars->v_full[stage], phase);
+#pragma unroll
+        for (int si = 0; si < NI; ++si) {
+          const int s = s_lo + si;
+          VP_SVC_WAIT(&bars->p_full[s][j & 1], (j >> 1) & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            // V tile [64 keys][64 d] as MN-major B: 8-key groups are 1024 B apart, 16 keys per MMA = 2048 B
+            const uint64_t pdesc = make_desc_sw128(sp + (s * 2 + (j & 1)) * P_BYTES, 1024, 0);
+            const uint64_t vdesc = make_desc_sw128(sv + stage * KV_BYTES, 1024, 1024);
+#pragma unroll
+            for (int k = 0; k < BKV / 16; ++k)
+              mma_ss(tmem_base + s * COL_STREAM + COL_O, pdesc + 2 * k, vdesc + (uint64_t)(128 * k), idesc_pv, (j | k) != 0);
+            tc_commit(&bars->o_done[s][j & 1]);
+            if (si == NI - 1) tc_commit(&bars->v_empty[stage]);        // one arrival per tile from each P V issuer
+          }
+          __syncwarp();
+          VP_TRACE(16 + svc, j, s & 3);
+        }
+        if (++stage == ST) { stage = 0; phase ^= 1; }
       }
     }
   }
@@ -471,8 +562,7 @@ int make_map3(CUtensorMap* map, const void* ptr, long long bh, long long len, in
 
 }  // namespace
 
-
-int launch_attention_v2(const void* q, const void* k0, const void* v0, const void* k1, const void* v1, const AttnParams& p_in,
+int launch_attention_v4(const void* q, const void* k0, const void* v0, const void* k1, const void* v1, const AttnParams& p_in,
                         cudaStream_t st) {
   AttnParams p = p_in;
   p.one = 1.0f;
