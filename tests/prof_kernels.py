@@ -80,6 +80,12 @@ def main():
            4.0 * M * D, "gbs")
     x3 = x.view(B, S, D)
     timeit("ln_modulate_copy_for_scale", lambda: xo.copy_(x3), 4.0 * M * D, "gbs")   # same bytes moved by a plain device copy
+    # all adaLN-zero tables of one backbone forward: 42 blocks x 2 LayerNormZero x [18432, 512] bf16 = 1.59 GB of weights
+    n_ada = 42 * 2 * 6 * D
+    w_ada, b_ada = torch.empty(n_ada, 512, dtype=BF16, device=dev).normal_(0, 0.02), rn(n_ada)
+    temb = torch.randn(B, 512, device=dev)
+    tab = torch.empty(B, n_ada, dtype=torch.float32, device=dev)
+    timeit("gemv_adaln_tables", lambda: ops.gemv(temb, w_ada, b_ada, True, out=tab), 2.0 * n_ada * 512, "gbs")
     # the library GEMM / SDPA of this box, for scale only (not part of the product path)
     wt = w1.t().contiguous()
     timeit("cublas_ff1_for_scale", lambda: torch.matmul(x, wt), 2.0 * M * 4 * D * D, "tflops")

@@ -113,3 +113,30 @@ def test_forward_signatures_equal_reference():
     assert RT.forward is not orig and RB.forward.__name__ == "branch_forward"
     vp.uninstall()
     assert RT.forward is orig
+
+
+def test_torch_ops_registered_with_the_c_prototypes():
+    """csrc/torch_ops.cpp: every compute entry point of the header is a torch.ops.vp_b200 op whose schema is the C prototype
+    minus the trailing stream (pointer -> Tensor?, pointer array -> int[], integer -> int, float -> float)."""
+    from videopainter_b200.build import build, TORCH_LIB
+    from videopainter_b200._lib import SIGNATURES
+    build()
+    torch.ops.load_library(TORCH_LIB)
+    assert torch.ops.vp_b200.version() >= 100
+    hdr = open(os.path.join(ROOT, "include", "vp_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    host_only = {"vp_peer_alloc", "vp_peer_open", "vp_peer_close", "vp_peer_free", "vp_peer_set_timeout_ms"}
+    n_ops = 0
+    for name in SIGNATURES:
+        if name in host_only:
+            continue
+        proto = re.search(r"\b" + name + r"\s*\((.*?)\)\s*;", hdr, flags=re.S).group(1)
+        params = [a.strip() for a in proto.split(",") if a.strip()]
+        assert params[-1].endswith("stream"), name
+        schema = getattr(torch.ops.vp_b200, name[3:]).default._schema
+        assert len(schema.arguments) == len(params) - 1, name
+        for a, c in zip(schema.arguments, params[:-1]):
+            want = "List[int]" if "* const*" in c else ("Optional[Tensor]" if "*" in c else ("float" if c.startswith("float") else "int"))
+            assert str(a.type) == want, (name, c, str(a.type))
+        n_ops += 1
+    assert n_ops == 18
