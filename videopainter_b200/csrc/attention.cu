@@ -80,6 +80,10 @@ constexpr float RESCALE_THRESHOLD = VP_ATTN_RESCALE_LOG2;   // log2 units
 #endif
 constexpr int NMMA = VP_ATTN_MMA_WARPS;
 static_assert(NMMA == 1 || NMMA == 2, "one or two MMA-issuing warps");
+#ifndef VP_ATTN_OPTIMISTIC
+#define VP_ATTN_OPTIMISTIC 0                 // 1: exponentials against the maximum in use, the tile's maximum verified after
+                                             //    (bit-identical; measured 2 % SLOWER: 8.79 vs 8.59 - 8.75 ms, in-step 10.49 vs 10.33)
+#endif
 #ifndef VP_ATTN_TRACE
 #define VP_ATTN_TRACE 0                      // 1: CTA (0, 0) records clock64() at the phase boundaries of its first tiles
 #endif
@@ -232,6 +236,107 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       tmem_wait_ld_dep64(sr);
       VP_TRACE(warp, j, 2);
 
+#if VP_ATTN_OPTIMISTIC
+      // Experiment kept for the record (off by default, see above): taking the row-maximum scan off the softmax warps'
+      // critical path does not help — the scan is not what the S round trip waits for.
+      // Optimistic reference maximum: the exponentials of tile j are issued at once against the maximum in use (m_used)
+      // while the tile's own maximum is reduced in their shadow (the scan costs issue slots, not MUFU slots); only when the
+      // maximum turns out to have grown by more than the threshold is the tile redone (S columns [32, 64) are still in TMEM,
+      // [0, 32) are kept in registers) after O and the row sum have been rescaled.  Tile 0 scans first.  Results are
+      // bit-identical to scanning first: the same reference maximum is used for every tile either way.
+      auto mask_ragged = [&](int lo) {
+        if (j == rag0 || j == rag1) {                         // ragged last tile of a segment
+          const int v = (j == rag0) ? val0 : val1;
+          if (v < BKV) {
+#pragma unroll
+            for (int i = lo; i < 64; ++i)
+              if (i >= v) sr[i] = 0xff800000u;                // -inf
+          }
+        }
+      };
+      mask_ragged(0);
+      if (j == 0) {
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 64; i += 8) {
+          mx0 = max3(mx0, __uint_as_float(sr[i + 0]), __uint_as_float(sr[i + 1]));
+          mx1 = max3(mx1, __uint_as_float(sr[i + 2]), __uint_as_float(sr[i + 3]));
+          mx2 = max3(mx2, __uint_as_float(sr[i + 4]), __uint_as_float(sr[i + 5]));
+          mx3 = max3(mx3, __uint_as_float(sr[i + 6]), __uint_as_float(sr[i + 7]));
+        }
+        m_used = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      }
+      VP_TRACE(warp, j, 3);
+      uint64_t acc0, acc1;
+#pragma unroll 1
+      for (int pass = 0;; ++pass) {
+        const float neg_mc = -m_used * c;
+        const uint64_t nmc2 = pack2(neg_mc, neg_mc);
+        acc0 = pack2(0.f, 0.f);
+        acc1 = pack2(0.f, 0.f);
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+        constexpr int CP = VP_ATTN_CHUNK_PAIRS;
+#pragma unroll
+        for (int ch = 0; ch < 32 / CP; ++ch) {
+          uint32_t pk[CP];
+          uint64_t y2[CP];
+#pragma unroll
+          for (int pr = 0; pr < CP; ++pr)
+            y2[pr] = fma2(pack2(__uint_as_float(sr[(ch * CP + pr) * 2]), __uint_as_float(sr[(ch * CP + pr) * 2 + 1])), c2v, nmc2);
+#pragma unroll
+          for (int pr = 0; pr < CP; ++pr) {
+            float e0, e1;
+            if ((pr & 7) < VP_ATTN_POLY_PER8) {
+              exp2_poly2(y2[pr], one2, e0, e1);
+            } else {
+              float y0, y1;
+              unpack2(y2[pr], y0, y1);
+              e0 = fast_exp2(y0);
+              e1 = fast_exp2(y1);
+            }
+            pk[pr] = pack_bf16(e0, e1);
+            if (pr & 1) acc1 = fma2(pack2(e0, e1), one2, acc1);
+            else acc0 = fma2(pack2(e0, e1), one2, acc0);
+            const int i = (ch * CP + pr) * 2;
+            if (pr & 1) mx1 = max3(mx1, __uint_as_float(sr[i]), __uint_as_float(sr[i + 1]));
+            else mx0 = max3(mx0, __uint_as_float(sr[i]), __uint_as_float(sr[i + 1]));
+          }
+          if (CP == 4) tmem_st_x4(tS + ch * CP, pk);
+          else if (CP == 8) tmem_st_x8(tS + ch * CP, pk);
+          else tmem_st_x16(tS + ch * CP, pk);
+        }
+        const float tile_max = fmaxf(mx0, mx1);
+        const bool need = (tile_max - m_used) * c > RESCALE_THRESHOLD;
+        if (!__any_sync(0xffffffffu, need)) break;                     // always taken in the second pass
+        float factor = 1.0f;
+        if (need) {
+          factor = fast_exp2((m_used - tile_max) * c);
+          m_used = tile_max;
+          row_sum *= factor;
+        }
+        mbar_wait_a(a_o_done, (j - 1) & 1);                            // j >= 1 here: P_{j-1} V_{j-1} has landed in O
+        tc_fence_after();
+        tmem_wait_st();                                                // the first pass' P stores, before S is read again
+#pragma unroll 1
+        for (int c8 = 0; c8 < DH; c8 += 8) {
+          uint32_t o[8];
+          tmem_ld_x8(tO + c8, o);
+          tmem_wait_ld();
+          asm volatile("" : "+r"(o[0]), "+r"(o[1]), "+r"(o[2]), "+r"(o[3]), "+r"(o[4]), "+r"(o[5]), "+r"(o[6]), "+r"(o[7]));
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+          tmem_st_x8(tO + c8, o);
+        }
+        tmem_ld_x32(tS + 32, sr + 32);                                 // columns [32, 64) of S were not overwritten by P
+        tmem_wait_ld_dep32(sr + 32);
+        mask_ragged(32);
+      }
+      {
+        float a0, a1;
+        unpack2(fma2(acc0, one2, acc1), a0, a1);
+        row_sum += a0 + a1;
+      }
+#else
       if (j == rag0 || j == rag1) {                           // ragged last tile of a segment
         const int v = (j == rag0) ? val0 : val1;
         if (v < BKV) {
@@ -317,6 +422,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         unpack2(fma2(acc0, one2, acc1), a0, a1);
         row_sum += a0 + a1;
       }
+#endif
       VP_TRACE(warp, j, 4);
       tmem_wait_st();
       tc_fence_before();

@@ -3,6 +3,7 @@
 // 2x2/stride-2 patch-embed convolution (EMB:408-414), mask pooling (EMB:417-426), the final double LayerNorm
 // (T3D:613-624) and unpatchify (T3D:630-632).
 #include "elementwise.cuh"
+#include <string.h>
 
 #include <stdlib.h>
 
@@ -218,6 +219,202 @@ __global__ void __launch_bounds__(WARPS * 32, LN_CTAS) ln_modulate_kernel(const 
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Second organisation of the same operation (the default; VP_B200_LN=cols selects the column-owner kernel above): a WARP
+// owns LNW_ROWS whole rows, so the two row statistics are warp shuffles — no block-wide reduction and no __syncthreads in
+// the row loop (the column-owner kernel spends ~195 instructions per row and thread around its four barriers per unit and
+// is issue-bound at 66 % of the HBM rate; here a row costs ~700 warp instructions instead of ~2300).
+//   * every warp has its own ring of LNW stages in shared memory, filled by bulk async copies (one contiguous copy per
+//     unit of LNW_ROWS rows) that one lane issues — the next unit streams in while the current one is processed, without
+//     costing registers (holding the rows in registers was tried: ptxas keeps the unpacked copy of every pass alive, 252
+//     registers for two rows);
+//   * the three passes (sum; centred squares; output) read the packed rows from shared memory, 16 bytes per lane;
+//   * the per-column coefficients A = gamma (1 + scale), C = beta (1 + scale) + shift of the CTA's (batch, expert) segment
+//     are built once per CTA in shared memory (fp32, laid out so that a lane's two float4 per 16-byte column group are
+//     conflict-free) and read once per LNW_ROWS rows — the round-1 warp-per-row kernel re-read 36 KB of parameters through
+//     L1 per 6 KB row.  CTAs are assigned to (batch, expert) segments in proportion to their rows.
+// Measured at [2 x 17 776, 3072] (B200, L2 flushed, a plain device copy of the same bytes: 73.7 us = 5.93 TB/s):
+//   column-owner kernel 88.1 us;  this kernel with 8 warps x 2 rows x 2 stages 98.3 us (ncu: 2 warps per scheduler, one
+//   instruction per 5.2 clk and warp: latency-bound),  16 warps x 2 rows x 1 stage 90.1 us,  16 warps x 1 row x 2 stages
+//   81.9 us = 5.33 TB/s (the default);  inside the power-capped step 8.21 ms for 440 launches vs 8.78 ms (4.68 vs 4.38 TB/s).
+// Shared-memory traffic per row at D = 3072: 6 KB written by the copy, 18 KB read by the passes, 24 KB / LNW_ROWS of
+// coefficients.
+// ------------------------------------------------------------------------------------------------------------------
+#ifndef VP_LNW_ROWS
+#define VP_LNW_ROWS 1
+#define VP_LNW_WARPS 16
+#endif
+constexpr int LNW_ROWS = VP_LNW_ROWS;     // rows per unit (one bulk copy, one read of the coefficients)
+constexpr int LNW_WARPS = VP_LNW_WARPS;
+constexpr int LNW_MAX_STAGES = 3;
+constexpr int LNW_MAX_SEGS = 16;
+constexpr int LNW_SMEM_BUDGET = 222 * 1024;
+struct LnSegs {
+  int n;
+  int cta0[LNW_MAX_SEGS + 1];      // first CTA of segment i; cta0[n] = grid
+  int batch[LNW_MAX_SEGS], text[LNW_MAX_SEGS], row0[LNW_MAX_SEGS], nrows[LNW_MAX_SEGS];
+};
+
+__device__ __forceinline__ uint64_t lnw_pack2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};\n" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void lnw_unpack2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;\n" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t lnw_fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;\n" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t lnw_add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;\n" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// one 32-bit word of two bf16 -> (low element, high element) as an fp32 pair
+__device__ __forceinline__ uint64_t lnw_pair(uint32_t w) { return lnw_pack2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); }
+
+template <int CH>   // 16-byte column groups per lane: D <= CH * 256
+__global__ void __launch_bounds__(LNW_WARPS * 32, 1) ln_rows_kernel(const LnModParams p, const LnSegs segs, int stages) {
+  extern __shared__ __align__(128) uint8_t lnw_smem[];               // A | C (fp32, permuted) | ring [warp][stage][rows][D] bf16
+  __shared__ uint64_t full[LNW_WARPS][LNW_MAX_STAGES];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int D = p.D, nchunk = D >> 3, halfD = D >> 1;
+  const uint32_t row_bytes = (uint32_t)D * 2u, stage_bytes = row_bytes * LNW_ROWS;
+  int seg = 0;
+  while (seg + 1 < segs.n && (int)blockIdx.x >= segs.cta0[seg + 1]) ++seg;
+  const int b = segs.batch[seg], text = segs.text[seg], seg_row0 = segs.row0[seg], nrows = segs.nrows[seg];
+  const int cta_in_seg = blockIdx.x - segs.cta0[seg], ctas_in_seg = segs.cta0[seg + 1] - segs.cta0[seg];
+  float* tA = reinterpret_cast<float*>(lnw_smem);
+  float* tC = tA + D;
+  uint8_t* ring = lnw_smem + (size_t)2 * D * sizeof(float) + (size_t)warp * stages * stage_bytes;
+
+  const int units = (nrows + LNW_ROWS - 1) / LNW_ROWS;
+  const int u_first = cta_in_seg * LNW_WARPS + warp, u_step = ctas_in_seg * LNW_WARPS;
+  const __nv_bfloat16* xseg = p.x + ((long long)b * p.x_batch_rows + p.x_row_offset + seg_row0) * D;
+  auto fetch = [&](int u, int stage) {                               // one lane: the unit's rows are contiguous in x
+    const int n = min(LNW_ROWS, nrows - u * LNW_ROWS);
+    mbar_arrive_expect_tx(&full[warp][stage], (uint32_t)n * row_bytes);
+    bulk_load(ring + (size_t)stage * stage_bytes, xseg + (long long)u * LNW_ROWS * D, (uint32_t)n * row_bytes, &full[warp][stage]);
+  };
+  if (lane == 0) {
+    for (int i = 0; i < stages; ++i) mbar_init(&full[warp][i], 1);
+    fence_barrier_init();
+    for (int i = 0; i < stages; ++i)
+      if (u_first + i * u_step < units) fetch(u_first + i * u_step, i);
+  }
+
+  // element k = 8c + 4h + e of a coefficient table lives at h * D/2 + 4c + e: lane c reads float4 c of each half
+  for (int c = threadIdx.x; c < nchunk; c += LNW_WARPS * 32) {
+    float g[8], be[8], A[8], C[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(p.gamma) + c), g);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(p.beta) + c), be);
+    if (p.mod) {
+      const float* sh = p.mod + (long long)b * p.mod_batch_stride + (text ? p.shift_text_off : p.shift_video_off) + c * 8;
+      const float* sc = p.mod + (long long)b * p.mod_batch_stride + (text ? p.scale_text_off : p.scale_video_off) + c * 8;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float one_plus = 1.f + __ldg(sc + e);
+        A[e] = g[e] * one_plus;
+        C[e] = fmaf(be[e], one_plus, __ldg(sh + e));
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { A[e] = g[e]; C[e] = be[e]; }
+    }
+    *reinterpret_cast<float4*>(tA + c * 4) = make_float4(A[0], A[1], A[2], A[3]);
+    *reinterpret_cast<float4*>(tA + halfD + c * 4) = make_float4(A[4], A[5], A[6], A[7]);
+    *reinterpret_cast<float4*>(tC + c * 4) = make_float4(C[0], C[1], C[2], C[3]);
+    *reinterpret_cast<float4*>(tC + halfD + c * 4) = make_float4(C[4], C[5], C[6], C[7]);
+  }
+  __syncthreads();
+
+  const float invD = 1.0f / (float)D;
+  int stage = 0;
+  uint32_t phase = 0;
+  for (int u = u_first; u < units; u += u_step) {
+    const int r0 = u * LNW_ROWS;
+    const int n = min(LNW_ROWS, nrows - r0);
+    __nv_bfloat16* y = p.y + ((long long)b * p.rows_per_batch + seg_row0 + r0) * D;
+    const uint8_t* src = ring + (size_t)stage * stage_bytes + (size_t)lane * 16;
+    while (!mbar_try_wait(&full[warp][stage], phase)) {}            // a bulk copy always completes
+    float mean[LNW_ROWS], rstd[LNW_ROWS];
+#pragma unroll
+    for (int r = 0; r < LNW_ROWS; ++r) {                              // pass 1: sums
+      uint64_t a0 = lnw_pack2(0.f, 0.f), a1 = a0;
+      if (r < n) {
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+          if (lane + i * 32 < nchunk) {
+            const uint4 w = *reinterpret_cast<const uint4*>(src + (size_t)r * row_bytes + i * 512);
+            a0 = lnw_add2(a0, lnw_add2(lnw_pair(w.x), lnw_pair(w.y)));
+            a1 = lnw_add2(a1, lnw_add2(lnw_pair(w.z), lnw_pair(w.w)));
+          }
+        }
+      }
+      float lo, hi;
+      lnw_unpack2(lnw_add2(a0, a1), lo, hi);
+      mean[r] = warp_sum(lo + hi) * invD;
+    }
+#pragma unroll
+    for (int r = 0; r < LNW_ROWS; ++r) {                              // pass 2: centred squares
+      const uint64_t nm2 = lnw_pack2(-mean[r], -mean[r]);
+      uint64_t q0 = lnw_pack2(0.f, 0.f), q1 = q0;
+      if (r < n) {
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+          if (lane + i * 32 < nchunk) {
+            const uint4 w = *reinterpret_cast<const uint4*>(src + (size_t)r * row_bytes + i * 512);
+            const uint64_t d0 = lnw_add2(lnw_pair(w.x), nm2), d1 = lnw_add2(lnw_pair(w.y), nm2);
+            const uint64_t d2 = lnw_add2(lnw_pair(w.z), nm2), d3 = lnw_add2(lnw_pair(w.w), nm2);
+            q0 = lnw_fma2(d0, d0, q0); q1 = lnw_fma2(d1, d1, q1);
+            q0 = lnw_fma2(d2, d2, q0); q1 = lnw_fma2(d3, d3, q1);
+          }
+        }
+      }
+      float lo, hi;
+      lnw_unpack2(lnw_add2(q0, q1), lo, hi);
+      rstd[r] = rsqrtf(warp_sum(lo + hi) * invD + p.eps);
+    }
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {                                    // pass 3: normalise, modulate, store
+      const int c = lane + i * 32;
+      if (c < nchunk) {
+        const float4 A0 = *reinterpret_cast<const float4*>(tA + c * 4), A1 = *reinterpret_cast<const float4*>(tA + halfD + c * 4);
+        const float4 C0 = *reinterpret_cast<const float4*>(tC + c * 4), C1 = *reinterpret_cast<const float4*>(tC + halfD + c * 4);
+        const uint64_t Ax = lnw_pack2(A0.x, A0.y), Ay = lnw_pack2(A0.z, A0.w), Az = lnw_pack2(A1.x, A1.y), Aw = lnw_pack2(A1.z, A1.w);
+        const uint64_t Cx = lnw_pack2(C0.x, C0.y), Cy = lnw_pack2(C0.z, C0.w), Cz = lnw_pack2(C1.x, C1.y), Cw = lnw_pack2(C1.z, C1.w);
+#pragma unroll
+        for (int r = 0; r < LNW_ROWS; ++r) {
+          if (r < n) {
+            const uint4 w = *reinterpret_cast<const uint4*>(src + (size_t)r * row_bytes + i * 512);
+            const uint64_t rs2 = lnw_pack2(rstd[r], rstd[r]);
+            const float nmr = -mean[r] * rstd[r];
+            const uint64_t nmr2 = lnw_pack2(nmr, nmr);
+            float o0, o1, o2, o3, o4, o5, o6, o7;
+            lnw_unpack2(lnw_fma2(lnw_fma2(lnw_pair(w.x), rs2, nmr2), Ax, Cx), o0, o1);
+            lnw_unpack2(lnw_fma2(lnw_fma2(lnw_pair(w.y), rs2, nmr2), Ay, Cy), o2, o3);
+            lnw_unpack2(lnw_fma2(lnw_fma2(lnw_pair(w.z), rs2, nmr2), Az, Cz), o4, o5);
+            lnw_unpack2(lnw_fma2(lnw_fma2(lnw_pair(w.w), rs2, nmr2), Aw, Cw), o6, o7);
+            uint4 out;
+            out.x = pack_bf16(o0, o1); out.y = pack_bf16(o2, o3); out.z = pack_bf16(o4, o5); out.w = pack_bf16(o6, o7);
+            *reinterpret_cast<uint4*>(y + (long long)r * D + c * 8) = out;
+          }
+        }
+      }
+    }
+    __syncwarp();                                                     // every lane has read its part of the stage
+    if (lane == 0) {
+      const int nxt = u + stages * u_step;
+      if (nxt < units) {
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic reads above before the async write below
+        fetch(nxt, stage);
+      }
+    }
+    if (++stage == stages) { stage = 0; phase ^= 1; }
+  }
+}
+
 // Final head normalisation: y = LN2(LN1(x)) * (1 + scale[b]) + shift[b] on the video rows only (T3D:613-624).
 template <int CH>
 __global__ void __launch_bounds__(256) ln_double_kernel(const LnModParams p) {
@@ -295,62 +492,77 @@ __global__ void __launch_bounds__(256) ln_double_kernel(const LnModParams p) {
 
 // ------------------------------------------------------------------------------------------------------------------
 // out[b, n] = sum_k act(in[b, k]) * W[n, k] + bias[n]   (fp32 in/out, bf16 weights).  Weight-bandwidth bound: the adaLN
-// tables of one forward stream 1.66 GB of weights through it (44 blocks x 2 x [18432, 512] bf16).
-// The activations (batch <= 8 rows of K floats) are transformed ONCE per CTA into shared memory — the first version
-// evaluated SiLU per (output row, batch, k), i.e. 1024 expf per 1 KiB of weights, and was MUFU-bound at 28 % of the HBM rate.
-// Each warp owns GEMV_RPW output rows, so that four independent 16-byte weight loads per lane are in flight.
+// tables of one forward stream 1.6 GB of weights through it (44 blocks x 2 x [18432, 512] bf16, i.e. 1 KiB rows).
+//   * the activations (batch <= 8 rows of K floats) go through the optional SiLU ONCE per CTA into shared memory (the
+//     first version evaluated 1024 expf per KiB of weights: MUFU-bound at 28 % of the HBM rate), stored so that the two
+//     float4 a lane needs per 16-byte weight load are conflict-free: element k = 8g + 4c + e lives at c * K/2 + 4g + e;
+//   * EIGHT lanes per output row, four rows per warp: one warp-wide 16-byte load covers 128 contiguous bytes of four rows,
+//     the cross-lane reduction is three shuffles per (row, batch) — with a whole warp per 1 KiB row it was five, and the
+//     reduce phase (no loads in flight) took as long as the loads;
+//   * eight independent 16-byte loads per lane are issued before the first is used (4 KiB in flight per warp);
+//   * persistent CTAs, grid-stride over the row groups.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int GEMV_MAX_B = 8;
-constexpr int GEMV_RPW = 4;
 constexpr int GEMV_WARPS = 8;
-__global__ void __launch_bounds__(GEMV_WARPS * 32) gemv_kernel(const float* __restrict__ in, const __nv_bfloat16* __restrict__ W,
-                                                               const __nv_bfloat16* __restrict__ bias, float* __restrict__ out,
-                                                               int B, int N, int K, int act_silu) {
-  extern __shared__ float gemv_x[];                                  // [B][K] activations after the optional SiLU
+constexpr int GEMV_ROWS_PER_WARP = 4;
+constexpr int GEMV_LOADS = 8;                                         // 16-byte weight loads in flight per lane
+template <int BT>
+__global__ void __launch_bounds__(GEMV_WARPS * 32, 4) gemv_kernel(const float* __restrict__ in, const __nv_bfloat16* __restrict__ W,
+                                                                  const __nv_bfloat16* __restrict__ bias, float* __restrict__ out,
+                                                                  int B, int N, int K, int act_silu) {
+  extern __shared__ float gemv_x[];                                  // [B][K] activations after the optional SiLU, permuted
+  const int halfK = K >> 1;
   for (int i = threadIdx.x; i < B * K; i += GEMV_WARPS * 32) {
+    const int b = i / K, k = i - b * K;
     const float v = in[i];
-    gemv_x[i] = act_silu ? silu(v) : v;
+    gemv_x[b * K + ((k >> 2) & 1) * halfK + (k >> 3) * 4 + (k & 3)] = act_silu ? silu(v) : v;
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // grid-stride over groups of GEMV_RPW rows: a CTA lives for many groups, so the activation transform above and the CTA
-  // launch are amortised (one CTA per 32 rows spent most of its short life in them: 2.5 TB/s)
-  for (int n0 = (blockIdx.x * GEMV_WARPS + warp) * GEMV_RPW; n0 < N; n0 += gridDim.x * GEMV_WARPS * GEMV_RPW) {
-  float acc[GEMV_RPW][GEMV_MAX_B];
+  const int sub = lane & 7, rg = lane >> 3;                          // lane `sub` of the eight that share row `rg` of the warp
+  const int groups = K >> 3;                                         // 16-byte groups per row
+  for (long long n0 = (long long)(blockIdx.x * GEMV_WARPS + warp) * GEMV_ROWS_PER_WARP; n0 < N;
+       n0 += (long long)gridDim.x * GEMV_WARPS * GEMV_ROWS_PER_WARP) {
+    const long long n = n0 + rg < N ? n0 + rg : N - 1;               // rows past the end re-read the last row (not stored)
+    const __nv_bfloat16* wrow = W + n * K;
+    float acc[BT];
 #pragma unroll
-  for (int r = 0; r < GEMV_RPW; ++r)
+    for (int b = 0; b < BT; ++b) acc[b] = 0.f;
+    for (int g0 = 0; g0 < groups; g0 += 8 * GEMV_LOADS) {
+      uint4 w[GEMV_LOADS];
 #pragma unroll
-    for (int b = 0; b < GEMV_MAX_B; ++b) acc[r][b] = 0.f;
-  for (int k0 = lane * 8; k0 < K; k0 += 256) {
-    float wf[GEMV_RPW][8];
+      for (int j = 0; j < GEMV_LOADS; ++j) {
+        const int g = g0 + j * 8 + sub;
+        w[j] = g < groups ? ldg_nc_v4(wrow + g * 8) : make_uint4(0u, 0u, 0u, 0u);
+      }
 #pragma unroll
-    for (int r = 0; r < GEMV_RPW; ++r) {
-      const int n = n0 + r < N ? n0 + r : N - 1;                       // rows past the end re-read the last row (not stored)
-      unpack8(ldg_nc_v4(W + (long long)n * K + k0), wf[r]);
-    }
+      for (int j = 0; j < GEMV_LOADS; ++j) {
+        const int g = g0 + j * 8 + sub;
+        if (g < groups) {
+          float wf[8];
+          unpack8(w[j], wf);
 #pragma unroll
-    for (int b = 0; b < GEMV_MAX_B; ++b) {
-      if (b < B) {
-        const float4 a0 = *reinterpret_cast<const float4*>(gemv_x + b * K + k0);
-        const float4 a1 = *reinterpret_cast<const float4*>(gemv_x + b * K + k0 + 4);
-        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-#pragma unroll
-        for (int r = 0; r < GEMV_RPW; ++r)
-#pragma unroll
-          for (int e = 0; e < 8; ++e) acc[r][b] = fmaf(a[e], wf[r][e], acc[r][b]);
+          for (int b = 0; b < BT; ++b) {
+            if (b < B) {
+              const float4 a0 = *reinterpret_cast<const float4*>(gemv_x + b * K + g * 4);
+              const float4 a1 = *reinterpret_cast<const float4*>(gemv_x + b * K + halfK + g * 4);
+              acc[b] = fmaf(a0.x, wf[0], acc[b]); acc[b] = fmaf(a0.y, wf[1], acc[b]);
+              acc[b] = fmaf(a0.z, wf[2], acc[b]); acc[b] = fmaf(a0.w, wf[3], acc[b]);
+              acc[b] = fmaf(a1.x, wf[4], acc[b]); acc[b] = fmaf(a1.y, wf[5], acc[b]);
+              acc[b] = fmaf(a1.z, wf[6], acc[b]); acc[b] = fmaf(a1.w, wf[7], acc[b]);
+            }
+          }
+        }
       }
     }
-  }
 #pragma unroll
-  for (int r = 0; r < GEMV_RPW; ++r) {
-#pragma unroll
-    for (int b = 0; b < GEMV_MAX_B; ++b) {
-      if (b < B) {
-        const float v = warp_sum(acc[r][b]);
-        if (lane == 0 && n0 + r < N) out[(long long)b * N + n0 + r] = v + (bias ? __bfloat162float(bias[n0 + r]) : 0.f);
-      }
+    for (int b = 0; b < BT; ++b) {
+      float v = acc[b];
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      if (b < B && sub == 0 && n0 + rg < N) out[(long long)b * N + n] = v + (bias ? __bfloat162float(bias[n]) : 0.f);
     }
-  }
   }
 }
 
@@ -608,6 +820,59 @@ int launch_ln_modulate(const LnModParams& p, cudaStream_t st) {
   LnModParams q = p;
   if (q.mod == nullptr || q.text_len < 0) q.text_len = 0;
   if (q.text_len > q.rows_per_batch) q.text_len = q.rows_per_batch;
+  VP_REQUIRE((reinterpret_cast<uintptr_t>(p.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 15) == 0, VP_ERR_BAD_ALIGN,
+             "ln_modulate: x and y must be 16-byte aligned");
+  static const bool cols = []() { const char* e = getenv("VP_B200_LN"); return e && !strcmp(e, "cols"); }();
+  const int batch_n = (int)(p.rows / p.rows_per_batch);
+  if (!cols && 2 * batch_n <= LNW_MAX_SEGS) {
+    const int sms_w = sm_count();
+    if (sms_w <= 0) return fail(VP_ERR_CUDA, "no CUDA device");
+    // CTAs per (batch, expert) segment in proportion to its rows, at least one, at most one per LNW_WARPS units
+    LnSegs sg{};
+    int seg_rows[LNW_MAX_SEGS];
+    for (int bi = 0; bi < batch_n; ++bi) {
+      if (q.text_len > 0) {
+        sg.batch[sg.n] = bi; sg.text[sg.n] = 1; sg.row0[sg.n] = 0; sg.nrows[sg.n] = q.text_len; seg_rows[sg.n++] = q.text_len;
+      }
+      if (q.rows_per_batch > q.text_len) {
+        sg.batch[sg.n] = bi; sg.text[sg.n] = 0; sg.row0[sg.n] = q.text_len; sg.nrows[sg.n] = q.rows_per_batch - q.text_len;
+        seg_rows[sg.n++] = q.rows_per_batch - q.text_len;
+      }
+    }
+    const long long budget = (long long)sms_w;                       // one CTA of LNW_WARPS warps per SM
+    int cta = 0;
+    for (int i = 0; i < sg.n; ++i) {
+      const int units = (seg_rows[i] + LNW_ROWS - 1) / LNW_ROWS;
+      long long want = (budget * seg_rows[i] + p.rows / 2) / p.rows;
+      const long long cap = (units + LNW_WARPS - 1) / LNW_WARPS;
+      if (want > cap) want = cap;
+      if (want < 1) want = 1;
+      sg.cta0[i] = cta;
+      cta += (int)want;
+    }
+    sg.cta0[sg.n] = cta;
+    const size_t tab_bytes = (size_t)2 * p.D * sizeof(float);
+    const size_t stage_all = (size_t)LNW_WARPS * LNW_ROWS * p.D * 2;  // one stage of every warp
+    int stages_w = (int)((LNW_SMEM_BUDGET - tab_bytes) / stage_all);
+    if (stages_w > LNW_MAX_STAGES) stages_w = LNW_MAX_STAGES;
+    const size_t smem_w = tab_bytes + (size_t)stages_w * stage_all;
+    const int ch = (p.D / 8 + 31) / 32;
+#define VP_LNW_CASE(N)                                                                                   \
+  if (ch <= N && stages_w >= 1) {                                                                        \
+    const int rc_w = configure_once(reinterpret_cast<const void*>(ln_rows_kernel<N>), LNW_SMEM_BUDGET);  \
+    if (rc_w) return rc_w;                                                                               \
+    ln_rows_kernel<N><<<(unsigned)cta, LNW_WARPS * 32, smem_w, st>>>(q, sg, stages_w);                   \
+    VP_CHECK_CUDA(cudaGetLastError());                                                                   \
+    return VP_OK;                                                                                        \
+  }
+    VP_LNW_CASE(1)
+    VP_LNW_CASE(2)
+    VP_LNW_CASE(4)
+    VP_LNW_CASE(8)
+    VP_LNW_CASE(12)
+    VP_LNW_CASE(16)
+#undef VP_LNW_CASE
+  }
   const int threads = ((p.D / 8 + 31) / 32) * 32;
   const int units_text = (q.text_len + LN_RB - 1) / LN_RB;
   const int units_video = (q.rows_per_batch - q.text_len + LN_RB - 1) / LN_RB;
@@ -638,16 +903,25 @@ int launch_gemv(const float* in, const void* W, const void* bias, float* out, in
   VP_REQUIRE(N > 0 && K > 0 && K % 8 == 0, VP_ERR_BAD_SHAPE, "gemv: K must be a multiple of 8");
   const size_t smem = (size_t)B * K * sizeof(float);
   VP_REQUIRE(smem <= 200 * 1024, VP_ERR_UNSUPPORTED, "gemv: batch x K activations do not fit in shared memory");
+  const void* fn = B == 1   ? reinterpret_cast<const void*>(gemv_kernel<1>)
+                   : B == 2 ? reinterpret_cast<const void*>(gemv_kernel<2>)
+                   : B <= 4 ? reinterpret_cast<const void*>(gemv_kernel<4>)
+                            : reinterpret_cast<const void*>(gemv_kernel<8>);
   if (smem > 48 * 1024) {
-    const int rc = configure_once(reinterpret_cast<const void*>(gemv_kernel), 200 * 1024);
+    const int rc = configure_once(fn, 200 * 1024);
     if (rc) return rc;
   }
-  const int rows_per_cta = GEMV_WARPS * GEMV_RPW;
+  const int rows_per_cta = GEMV_WARPS * GEMV_ROWS_PER_WARP;
   const int sms = sm_count();
   int grid = (N + rows_per_cta - 1) / rows_per_cta;
-  if (sms > 0 && grid > sms * 8) grid = sms * 8;
-  gemv_kernel<<<grid, GEMV_WARPS * 32, smem, st>>>(in, (const __nv_bfloat16*)W,
-                                                                                 (const __nv_bfloat16*)bias, out, B, N, K, act_silu);
+  if (sms > 0 && grid > sms * 4) grid = sms * 4;                       // persistent: 4 CTAs of 8 warps per SM
+  const __nv_bfloat16* w = (const __nv_bfloat16*)W;
+  const __nv_bfloat16* bs = (const __nv_bfloat16*)bias;
+  const unsigned threads = GEMV_WARPS * 32;
+  if (B == 1) gemv_kernel<1><<<grid, threads, smem, st>>>(in, w, bs, out, B, N, K, act_silu);
+  else if (B == 2) gemv_kernel<2><<<grid, threads, smem, st>>>(in, w, bs, out, B, N, K, act_silu);
+  else if (B <= 4) gemv_kernel<4><<<grid, threads, smem, st>>>(in, w, bs, out, B, N, K, act_silu);
+  else gemv_kernel<8><<<grid, threads, smem, st>>>(in, w, bs, out, B, N, K, act_silu);
   VP_CHECK_CUDA(cudaGetLastError());
   return VP_OK;
 }
