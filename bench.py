@@ -245,6 +245,8 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-eager", action="store_true")
     ap.add_argument("--breakdown", default=None, help="write the per-kernel breakdown JSON to this path")
+    ap.add_argument("--graphs", type=int, default=int(os.environ.get("VP_B200_GRAPH", "0")),
+                    help="1: the two forwards of a step are replayed from CUDA graphs (videopainter_b200/graphs.py)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -343,8 +345,9 @@ def main() -> None:
         out_host.copy_(noise.float(), non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
+    vp.enable_graphs(bool(args.graphs))
     with torch.no_grad():
-        for _ in range(args.warmup):
+        for _ in range(args.warmup):           # with graphs: eager, capture + replay, replay
             step(resident)
         # ---------------- device-resident timing (value): no per-op events, nothing but the step's own launches ----------------
         sampler = ClockSampler(local)
@@ -361,12 +364,16 @@ def main() -> None:
         # ---------------- end-to-end timing: host buffers in, host result out ----------------
         e2e_ms = timed(e2e_step)
         # ---------------- per-kernel pass: the same K steps with CUDA events around every launch (roofline / breakdown) --------
+        vp.enable_graphs(False)                  # events around every launch need the launches on the stream
         ops.start_profile()
         prof_ms_per_step = timed(resident_step)
         prof = ops.stop_profile()
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     d2h = out_host.numel() * out_host.element_size()
 
+    last.clear()
+    uses_p2p = bool(parallel.current() and parallel.current().p2p)
+    parallel.shutdown()                        # drops captured graphs: NCCL cannot finalise while graphs hold its collectives
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -415,14 +422,14 @@ def main() -> None:
            "config": {"workload": "CogVideoX-5B-I2V (42 layers, 48x64 heads) + 2-layer VideoPainter branch, one denoise step at "
                                   "49x480x720 (17776 tokens), CFG batch 2, return_hidden_states=True as PIPE:967-980",
                       "parallelism": plan.describe() + ((", all-to-all fused into the GEMM / attention epilogues over NVLink peer memory"
-                                                         if parallel.current().p2p else ", NCCL all-to-all") if plan.sp > 1 else ""),
+                                                         if uses_p2p else ", NCCL all-to-all") if plan.sp > 1 else ""),
                       "l2": "per-step working set (11.7 GB weights, 218 MB activations per "
                       "layer) exceeds the 126 MB L2; no explicit flush", "random_init": True},
            "step_tflops": flops / (ms_per_step * 1e-3) / 1e12,
            "frac_of_bf16_peak": {"sustained": flops / (ms_per_step * 1e-3) / 1e12 / (peak_tf * world),
                                  "burst": flops / (ms_per_step * 1e-3) / 1e12 / (peaks.get("bf16_tflops", 1650.0) * world),
                                  "note": "whole-job algorithmic FLOP/s over n_gpus x the measured cuBLAS peak"},
-           "roofline": roofline, "clocks": clocks, "gpu_launches": launches,
+           "roofline": roofline, "clocks": clocks, "gpu_launches": launches, "cuda_graphs": bool(args.graphs),
            "noise_sha256": noise_sha, "noise_absmax": noise_absmax,
            "e2e": {"value": 1000.0 / e2e_ms, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                    "ms_per_step": e2e_ms}}

@@ -123,7 +123,9 @@ int vp_step_end(const void* noise_pred, float guidance, const void* sample, cons
  * h / (heads/peers)'s buffer at token rows [row_offset, row_offset + m) (q_out .. v2_out select the slot: they point into
  * the LOCAL buffer local_base); vp_attention_peer stores query row r into rank r / (seq_q/peers)'s output buffer at source
  * slot my_rank.  vp_peer_barrier orders the two: all earlier peer stores of every rank are visible to every rank after it
- * (system-scope release / acquire on per-rank flag words; epoch must increase by one per call, identically on all ranks). */
+ * (system-scope release / acquire on per-rank flag words; epoch must increase by one per call, identically on all ranks;
+ * epoch == 0: the kernel counts its own calls in word 9 of the rank's flag buffer instead, so that the launch does not
+ * depend on the call history and can be replayed from a CUDA graph — one flag buffer must stick to one of the two modes). */
 int vp_gemm_qkv_peer(const void* a, long long lda, const void* w, long long ldw, const void* bias, int m, int k, int heads,
                      int qkv_first, void* q_out, void* k_out, void* v_out, void* k2_out, void* v2_out, const uint8_t* mask2,
                      const float* row_scale, const void* norm_q_w, const void* norm_q_b, const void* norm_k_w,
@@ -136,7 +138,7 @@ int vp_attention_peer(const void* q, const void* k0, const void* v0, int kv_len0
 int vp_peer_barrier(void* const* peer_flags, int peers, int my_rank, unsigned int epoch, void* stream);
 /* The barrier's wait is bounded (default 20 000 ms, or the environment variable VP_B200_PEER_TIMEOUT_MS at first use; 0 = wait
  * for ever): a rank whose peers do not show up in time adds one to 32-bit word 8 of ITS flag buffer (the buffers are 64
- * bytes: words 0..7 = epochs written by the peers, word 8 = time-out count) and lets the stream continue — no trap, no
+ * bytes: words 0..7 = epochs written by the peers, word 8 = time-out count, word 9 = call count of the epoch == 0 mode) and lets the stream continue — no trap, no
  * sticky CUDA error; the host reads the word whenever it likes.  Kernel-replay profilers (ncu) stall single ranks for
  * longer than any sensible bound: profile peer mode with the timeout set to 0 and `--replay-mode application`. */
 int vp_peer_set_timeout_ms(long long ms);

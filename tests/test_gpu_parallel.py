@@ -104,4 +104,15 @@ def test_peer_buffer_is_zeroed_device_memory_viewed_without_copy():
     ops.peer_barrier([flags.ptr], 0, 2)
     torch.cuda.synchronize()
     assert int(flags.tensor.view(torch.int32)[0]) == 2
-    buf.free(); flags.free()
+    # epoch == 0: the kernel counts its own calls (word 9), which is what makes the launch replayable from a CUDA graph
+    auto = ops.PeerBuffer(64, torch.device("cuda", 0))
+    for _ in range(3):
+        ops.peer_barrier([auto.ptr], 0, 0)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        ops.peer_barrier([auto.ptr], 0, 0)
+    g.replay(); g.replay()
+    torch.cuda.synchronize()
+    words = auto.tensor.view(torch.int32)
+    assert int(words[0]) == 5 and int(words[9]) == 5 and int(words[8]) == 0      # 3 eager + 2 replays (capture does not run)
+    buf.free(); flags.free(); auto.free()

@@ -663,8 +663,18 @@ __global__ void __launch_bounds__(256) a2a_unpack_heads_kernel(const uint4* __re
 // counts the event in word kPeerErrWord of its own flag buffer and carries on — the host decides what to do; nothing traps.
 struct PeerFlags { uint32_t* p[8]; };
 constexpr int kPeerErrWord = 8;
+constexpr int kPeerCountWord = 9;     // epoch == 0: the epoch is this rank's own barrier count, kept in its flag buffer
 __global__ void peer_barrier_kernel(PeerFlags flags, int peers, int my_rank, uint32_t epoch, unsigned long long timeout_ns) {
   const int i = threadIdx.x;
+  if (epoch == 0) {
+    // Device-side epoch: nothing in the launch depends on how many barriers ran before, so the launch can be replayed from
+    // a CUDA graph.  Every rank runs the same sequence of barriers, hence the counts agree; launches of one stream are
+    // serialised, so the read-modify-write needs no atomics.
+    volatile uint32_t* count = flags.p[my_rank] + kPeerCountWord;
+    epoch = *count + 1;
+    __syncwarp();
+    if (i == 0) *count = epoch;
+  }
   if (i >= peers) return;
   __threadfence_system();
   asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(flags.p[i] + my_rank), "r"(epoch) : "memory");

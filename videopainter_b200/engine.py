@@ -225,7 +225,6 @@ class _Workspace:
             raw, self.ptrs_ao = self._share(rt, P * R * Hl * 64 * 2, device)
             self.ao_recv = raw.view(BF16).view(P, R, Hl * 64)
             self.flags, self.ptrs_flags = self._share(rt, 64, device)
-            self.epoch = 0
             # time-outs of the device barrier are counted in word PEER_ERR_WORD of the flag buffer; the count is copied to
             # pinned host memory after every forward and looked at, without synchronising, before the next one
             self.err_host = torch.zeros(1, dtype=torch.int32).pin_memory()
@@ -248,7 +247,7 @@ class _Workspace:
             self.peer = False
 
     def post_check(self):
-        if self.peer:
+        if self.peer and not torch.cuda.is_current_stream_capturing():     # a captured forward is checked around its replay (graphs.py)
             w = parallel.PEER_ERR_WORD
             self.err_host.copy_(self.flags.view(torch.int32)[w:w + 1], non_blocking=True)
             self.err_event = torch.cuda.Event()
@@ -256,7 +255,7 @@ class _Workspace:
 
     def poll_check(self, wait: bool = False):
         """Raise if a device-side peer barrier of an earlier forward ran out of time (its results are invalid)."""
-        if not self.peer or self.err_event is None:
+        if not self.peer or self.err_event is None or torch.cuda.is_current_stream_capturing():
             return
         if wait:
             self.err_event.synchronize()
@@ -271,8 +270,7 @@ class _Workspace:
     def peer_sync(self):
         """All peer stores issued so far by every rank of the group are visible to every rank after this point of the
         stream."""
-        self.epoch += 1
-        self.rt.peer_barrier(self.ptrs_flags, self.epoch)
+        self.rt.peer_barrier(self.ptrs_flags, 0)        # 0: the kernel keeps the epoch itself (replayable from a CUDA graph)
 
     def second_kv(self):
         if self.k2 is None:
@@ -297,6 +295,8 @@ def _workspace(pm: PackedModel, B, S, Sv, sh: Shard, device, rt=None) -> _Worksp
         for old in pm.workspace.values():          # one shape at a time: a new shape releases the old buffers (peer memory too)
             old.close()
         pm.workspace.clear()
+        from . import graphs
+        graphs.clear(pm)                           # captured forwards hold the addresses of the buffers just released
         ws = _Workspace(pm, B, S, Sv, sh, device, rt)
         pm.workspace[key] = ws
     return ws

@@ -19,7 +19,7 @@ from typing import Any, Dict, List, Optional, Tuple, Union
 import torch
 import torch.nn as nn
 
-from . import engine
+from . import engine, graphs
 from .engine import Dims
 
 
@@ -259,6 +259,75 @@ def invalidate(m: nn.Module) -> None:
 
 
 # ------------------------------------------------------------------------------------------------------------------
+# CUDA-graph front ends of the two engine forwards (graphs.py): sort the arguments into copied / by-address / constant
+# ------------------------------------------------------------------------------------------------------------------
+def _timestep_tensor(timestep, batch: int, device) -> torch.Tensor:
+    if not torch.is_tensor(timestep):
+        return torch.full((batch,), timestep, dtype=torch.float32 if isinstance(timestep, float) else torch.int64, device=device)
+    t = timestep.to(device)
+    return t[None] if t.ndim == 0 else t
+
+
+def _graphed_transformer(pm, hidden_states, encoder_hidden_states, timestep, image_rotary_emb, attention_kwargs,
+                         branch_block_samples, branch_block_masks, add_first, return_hidden_states, return_resample_mask,
+                         id_pool_resample_learnable):
+    if not hidden_states.is_cuda:
+        raise RuntimeError("videopainter_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
+    kw = dict(attention_kwargs) if attention_kwargs else {}
+    prev = kw.get("prev_hidden_states")
+    prev_w = kw.get("prev_clip_weight")
+    prev_w = None if prev_w is None else float(prev_w)
+    samples = list(branch_block_samples) if branch_block_samples is not None else None
+    copied = {"x": hidden_states, "text": encoder_hidden_states,
+              "t": _timestep_tensor(timestep, hidden_states.shape[0], hidden_states.device), "masks": branch_block_masks,
+              "prm": kw.get("prev_resample_mask")}
+    for i, smp in enumerate(samples or ()):
+        copied[f"s{i}"] = smp
+    pinned = {}
+    if image_rotary_emb is not None:
+        pinned["rope0"], pinned["rope1"] = image_rotary_emb
+    prev_keys = tuple(sorted(prev)) if prev is not None else None
+    for i in prev_keys or ():
+        pinned[f"prev{i}"] = prev[i]
+    flags = (add_first, return_hidden_states, return_resample_mask, id_pool_resample_learnable, prev_w,
+             None if samples is None else len(samples), prev_keys, image_rotary_emb is None)
+
+    def fn(c, p):
+        akw = {}
+        if prev_keys is not None:
+            akw["prev_hidden_states"] = {i: p[f"prev{i}"] for i in prev_keys}
+        if prev_w is not None:
+            akw["prev_clip_weight"] = prev_w
+        if c["prm"] is not None:
+            akw["prev_resample_mask"] = c["prm"]
+        smp = None if samples is None else [c[f"s{i}"] for i in range(len(samples))]
+        rope = None if image_rotary_emb is None else (p["rope0"], p["rope1"])
+        return engine.transformer_forward(pm, c["x"], c["text"], c["t"], rope, akw, smp, c["masks"], add_first,
+                                          return_hidden_states, return_resample_mask, id_pool_resample_learnable)
+
+    out, hs, rmask = graphs.run(pm, "transformer", fn, copied, pinned, flags)
+    return out.clone(), hs, None if rmask is None else rmask.clone()
+
+
+def _graphed_branch(pm, hidden_states, encoder_hidden_states, branch_cond, timestep, image_rotary_emb, conditioning_scale,
+                    wo_text=False):
+    if not hidden_states.is_cuda:
+        raise RuntimeError("videopainter_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
+    copied = {"x": hidden_states, "text": encoder_hidden_states, "cond": branch_cond,
+              "t": _timestep_tensor(timestep, hidden_states.shape[0], hidden_states.device)}
+    pinned = {}
+    if image_rotary_emb is not None:
+        pinned["rope0"], pinned["rope1"] = image_rotary_emb
+    flags = (float(conditioning_scale), bool(wo_text), image_rotary_emb is None)
+
+    def fn(c, p):
+        rope = None if image_rotary_emb is None else (p["rope0"], p["rope1"])
+        return engine.branch_forward(pm, c["x"], c["text"], c["cond"], c["t"], rope, conditioning_scale, wo_text=wo_text)
+
+    return [o.clone() for o in graphs.run(pm, "branch", fn, copied, pinned, flags)]
+
+
+# ------------------------------------------------------------------------------------------------------------------
 # forwards with the reference signatures
 # ------------------------------------------------------------------------------------------------------------------
 def transformer_forward(self, hidden_states: torch.Tensor, encoder_hidden_states: torch.Tensor,
@@ -278,7 +347,8 @@ def transformer_forward(self, hidden_states: torch.Tensor, encoder_hidden_states
         raise NotImplementedError("self-guidance (T3D:593-594) is not used by the VideoPainter pipelines")
     lora_scale = (attention_kwargs or {}).get("scale", 1.0)     # T3D:490-498: scale_lora_layers(self, lora_scale)
     pm = packed_for(self, False, hidden_states.device, lora_scale)
-    out, hs, rmask = engine.transformer_forward(
+    run = _graphed_transformer if graphs.graphs_enabled() else engine.transformer_forward
+    out, hs, rmask = run(
         pm, hidden_states, encoder_hidden_states, timestep, image_rotary_emb, attention_kwargs, branch_block_samples,
         branch_block_masks, bool(add_first), bool(return_hidden_states), bool(return_resample_mask),
         bool(id_pool_resample_learnable))
@@ -300,8 +370,9 @@ def branch_forward(self, hidden_states: torch.Tensor, encoder_hidden_states: tor
         raise NotImplementedError("timestep_cond is not used by any CogVideoX checkpoint")
     lora_scale = (attention_kwargs or {}).get("scale", 1.0)     # BR:336-345
     pm = packed_for(self, True, hidden_states.device, lora_scale)
-    samples = engine.branch_forward(pm, hidden_states, encoder_hidden_states, branch_cond, timestep, image_rotary_emb,
-                                    conditioning_scale, wo_text=bool(wo_text))
+    run = _graphed_branch if graphs.graphs_enabled() else engine.branch_forward
+    samples = run(pm, hidden_states, encoder_hidden_states, branch_cond, timestep, image_rotary_emb,
+                  conditioning_scale, wo_text=bool(wo_text))
     samples = None if len(samples) == 0 else samples
     if not return_dict:
         return (samples,)

@@ -292,6 +292,10 @@ def install(rt: Optional[Runtime]) -> Optional[Runtime]:
 
 
 def shutdown() -> None:
+    """Forget the runtime of this thread.  Call BEFORE torch.distributed.destroy_process_group(): captured CUDA graphs that
+    contain NCCL collectives must be gone by then (graphs.clear_all)."""
+    from . import graphs
+    graphs.clear_all()
     _tls.runtime = None
 
 
