@@ -86,3 +86,35 @@ def test_installed_pipeline_matches_reference_on_gpu(resample):
     print(f"final latents: ours vs eager cos={_cos(ours_lat, eager_lat):.6f}; ours vs fp32 golden cos={_cos(ours_lat, gold['latents']):.6f}, "
           f"eager vs fp32 golden cos={_cos(eager_lat, gold['latents']):.6f}")
     assert _cos(ours_lat, eager_lat) >= 0.999
+
+
+@needs_ref
+@pytest.mark.gpu
+@pytest.mark.parametrize("resample", [False, True])
+def test_installed_pipeline_with_cuda_graphs_is_bit_identical(resample):
+    """The same pipeline run with every forward replayed from a CUDA graph (videopainter_b200/graphs.py): 8 transformer and 8
+    branch calls over two windows, the second carrying the first window's hidden-state list — handed out as views of the
+    graph's arena — through the pipeline's own plumbing (PIPE:982-988).  Same kernels, same arguments: every noise prediction
+    and the final latents must be bit-identical to the launches from Python."""
+    import videopainter_b200 as vp
+    from videopainter_b200 import graphs
+    ref = PA.load_reference()
+    bf16 = torch.bfloat16
+    vp.install()
+    try:
+        graphs.enable_graphs(False)
+        plain, plain_lat = PA.run(PA.build_pipeline(ref, "cuda", bf16, resample), resample)
+        graphs.enable_graphs(True)
+        pipe = PA.build_pipeline(ref, "cuda", bf16, resample)
+        graphed, graphed_lat = PA.run(pipe, resample)
+        pm = pipe.transformer.__dict__["_vp_packed"]["pm"]
+        st = graphs.stats(pm)
+        print("transformer graphs:", st)
+        assert st["captures"] >= 2 and st["replays"] >= 4          # one signature per window: eager, capture + replay, replays
+    finally:
+        graphs.enable_graphs(False)
+        vp.uninstall()
+    assert len(plain) == len(graphed) == 8
+    for i, (a, b) in enumerate(zip(graphed, plain)):
+        assert torch.equal(a, b), f"call {i}: max abs diff {float((a - b).abs().max())}"
+    assert torch.equal(graphed_lat, plain_lat)
