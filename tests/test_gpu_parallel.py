@@ -116,3 +116,27 @@ def test_peer_buffer_is_zeroed_device_memory_viewed_without_copy():
     words = auto.tensor.view(torch.int32)
     assert int(words[0]) == 5 and int(words[9]) == 5 and int(words[8]) == 0      # 3 eager + 2 replays (capture does not run)
     buf.free(); flags.free(); auto.free()
+
+
+def test_two_processes_on_one_gpu_exchange_through_ipc_and_the_device_barrier():
+    """The pieces the virtual-rank tests replace — CUDA-IPC mapping of a peer's buffer and the device-side barrier — run for
+    real between two processes that share this GPU (tests/ipc_pair_check.py), eagerly and from a CUDA graph."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29533")
+        procs.append(subprocess.Popen([sys.executable, os.path.join(root, "tests", "ipc_pair_check.py")], env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = []
+    for p in procs:
+        try:
+            out, _ = p.communicate(timeout=300)
+        except subprocess.TimeoutExpired:
+            p.kill()
+            out, _ = p.communicate()
+        outs.append(out)
+    for rank, (p, out) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and f"rank {rank}: ok" in out, out[-3000:]
