@@ -53,6 +53,7 @@ def main():
     ap.add_argument("--lora-rank", type=int, default=0)
     ap.add_argument("--prev-clip-weight", type=float, default=0.5)
     ap.add_argument("--guidance-scale", type=float, default=6.0)
+    ap.add_argument("--graphs", type=int, default=1, help="1: replay the forwards from CUDA graphs (videopainter_b200/graphs.py)")
     args = ap.parse_args()
 
     real_stdout = os.dup(1)
@@ -71,6 +72,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     plan = parallel.init(world, rank).plan
+    vp.enable_graphs(bool(args.graphs))
 
     torch.manual_seed(1234)
     tr = vp.CogVideoXTransformer3DModel(**dict(FULL, num_layers=args.layers), id_pool_resample_learnable=args.resample, device=dev, dtype=BF16)
@@ -157,10 +159,11 @@ def main():
     if rank == 0:
         total = sum(window_ms)
         rec = {"example": "inpaint_loop", "n_gpus": world, "parallelism": plan.describe(), "layers": args.layers, "steps": args.steps,
-               "windows": args.windows, "resample": args.resample, "lora_rank": args.lora_rank,
+               "windows": args.windows, "resample": args.resample, "lora_rank": args.lora_rank, "cuda_graphs": bool(args.graphs),
                "steps_per_s": args.steps * args.windows / (total / 1000.0), "window_ms": window_ms, "latents_sha256_16": digest,
                "ranks_agree": ok, "finite": bool(torch.isfinite(latents.float()).all())}
         os.write(real_stdout, (json.dumps(rec) + "\n").encode())
+    parallel.shutdown()          # drops the captured graphs: NCCL cannot finalise a communicator that a live graph still uses
     if world > 1:
         dist.destroy_process_group()
 

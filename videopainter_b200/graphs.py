@@ -76,6 +76,22 @@ def clear_all() -> None:
 atexit.register(clear_all)
 
 
+def _guard_process_group_teardown() -> None:
+    """torch.distributed.destroy_process_group() with live graphs hangs in NCCL: make it drop them first."""
+    import torch.distributed as dist
+    if not dist.is_available() or getattr(dist.destroy_process_group, "_vp_b200_guard", False):
+        return
+    original = dist.destroy_process_group
+
+    def destroy_process_group(*args, **kwargs):
+        clear_all()
+        return original(*args, **kwargs)
+
+    destroy_process_group._vp_b200_guard = True
+    destroy_process_group.__doc__ = original.__doc__
+    dist.destroy_process_group = destroy_process_group
+
+
 def stats(pm) -> Dict[str, int]:
     g = pm.__dict__.get("_graphs") or {}
     return {"graphs": len(g), "replays": pm.__dict__.get("_graph_replays", 0), "captures": pm.__dict__.get("_graph_captures", 0)}
@@ -115,6 +131,7 @@ def run(pm, kind: str, fn: Callable[[Dict[str, Any], Dict[str, Any]], Any], copi
         graphs[key] = ent
         if not any(r() is pm for r in _registry):
             _registry.append(weakref.ref(pm))
+            _guard_process_group_teardown()
         pm.__dict__["_graph_captures"] = pm.__dict__.get("_graph_captures", 0) + 1
     else:
         graphs.move_to_end(key)
