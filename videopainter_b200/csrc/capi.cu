@@ -121,8 +121,9 @@ int vp_gemm_gate_residual(const void* a, long long lda, const void* w, long long
   p.inject_mask = inject_mask; p.video_len = video_len;
   p.a_k_chunk = a_k_chunk; p.a_chunk_stride = a_chunk_stride;
   // rasterisation: the A panel of one m-group (group_m * 128 rows * K) has to stay in L2 next to W while the group walks over
-  // all n-tiles; with K = 12288 (FFN-2) 16 m-tiles are 50 MB and A was fetched 3-4 times from DRAM (ncu: 3.56 GB per launch)
-  if ((long long)k * 2 * 128 * 16 > (24ll << 20)) p.group_m = 8;
+  // all n-tiles; with K = 12288 (FFN-2) 16 m-tiles are 50 MB and A was fetched 3-4 times from DRAM (ncu: 3.56 GB per launch).
+  // CTA-pair kernel, stand-alone at M = 35552: group 2 / 4 / 8 / 16 / 32 = 1519 / 1512 / 1477 / 1500 / 1483 TFLOP/s
+  if ((long long)k * 2 * 128 * 16 > (24ll << 20)) p.group_m = 4;
   return launch_gemm(EPI_RESID, a, lda, w, ldw, p, (cudaStream_t)stream);
 }
 
