@@ -1,6 +1,7 @@
 """Opcode census of the built library per kernel (`cuobjdump -sass`), kept under profiles/ as the evidence that the hot
 kernels are Blackwell-native: UTC*MMA = tcgen05.mma, LDTM / STTM = tcgen05.ld / st, UTMALDG / UBLKCP = TMA, HMMA = legacy
-mma.sync (must be absent).   python tools/sass_summary.py > profiles/r2_sass_summary.txt"""
+mma.sync (must be absent); the `.2CTA` forms (UTCHMMA.2CTA, UTMALDG.*.2CTA, UTCBAR.2CTA.MULTICAST) are the CTA-pair GEMM.
+    python tools/sass_summary.py > profiles/r2_sass_summary.txt"""
 import collections
 import os
 import re
@@ -34,6 +35,8 @@ def main():
         tot.update(c)
         print(f"{k[:70]:70s} instr={sum(c.values()):6d} " + " ".join(f"{w}={c[w]}" for w in WATCH if c[w]))
     print("# whole library: " + " ".join(f"{w}={tot[w]}" for w in WATCH))
+    full = collections.Counter(re.findall(r"\b(UTCHMMA[.\w]*|UTMALDG[.\w]*|UTCBAR[.\w]*|UTCATOMSWS[.\w]*)", txt))
+    print("# tcgen05 / TMA opcodes with modifiers: " + " ".join(f"{k}={v}" for k, v in sorted(full.items())))
     assert tot["HMMA"] == 0 and tot["HGMMA"] == 0, "legacy tensor-core instructions found"
 
 
